@@ -1,0 +1,57 @@
+// Internal GEMM interfaces shared by the SIMT (gemm_simt.cu) and tcgen05 (gemm_tc.cu) paths.
+#pragma once
+#include "common.cuh"
+#include "prof.cuh"
+
+namespace gib {
+
+enum Epi : int {
+  EPI_ACT = 0,       // C = act(acc + bias)
+  EPI_MUL_DACT = 1,  // C = acc * act'(aux)      (aux = activation OUTPUT of the layer below)
+  EPI_ADD = 2        // C = acc + aux
+};
+
+// C[M, :N] = epi( A[M,K] * B[N,K]^T ).  A, B row-major, K-contiguous, K % 16 == 0,
+// lda/ldb % 4 == 0.  Columns [n_valid, n_store) are written as zeros; columns >= n_store
+// are not touched.
+struct GemmNT {
+  const float* A = nullptr; int lda = 0;
+  const float* B = nullptr; int ldb = 0;
+  float* C = nullptr; int ldc = 0;
+  int M = 0, N = 0, K = 0;
+  const float* bias = nullptr;
+  int act = ACT_NONE;
+  int mode = EPI_ACT;
+  const float* aux = nullptr; int ldaux = 0;
+  int n_store = 0;
+  int n_valid = 0;
+  double work = 0;   // algorithmic FLOPs of this launch (0: derive from the padded extents)
+};
+
+struct GemmTN {  // kernel-level args of the split-K dW kernel
+  const float* G; int ldg;
+  const float* X; int ldx;
+  int M, Nn, Kk, chunk_rows;
+  float* ws; float* ws_bias;
+};
+
+// dW[r, c] += sum_m G[m, prow(r)] * X[m, c];  dbias[r] += sum_m G[m, prow(r)]
+// prow(r) = (r / Rb) * Rbp + r % Rb maps a real output row to its padded (gate-blocked) row.
+// Destination element (r, c) lives at dW[r * rs + c * cs] (handles MNN's strided weights).
+struct GemmDW {
+  const float* G = nullptr; int ldg = 0; int Nn = 0;  // G: [M, Nn] padded width
+  const float* X = nullptr; int ldx = 0; int Kk = 0;  // X: [M, Kk] padded width
+  int M = 0;
+  float* dW = nullptr; float* dbias = nullptr;        // either may be null
+  int R = 0, C = 0, Rb = 0, Rbp = 0;
+  long long rs = 0, cs = 1;
+  float* scratch = nullptr;                           // >= gemm_dw_scratch_floats(M, Nn, Kk)
+  double work = 0;                                    // algorithmic FLOPs (0: derive)
+};
+
+int gemm_nt(const GemmNT& p, cudaStream_t st);
+int gemm_dw(const GemmDW& q, cudaStream_t st);
+void gemm_dw_plan(int M, int Nn, int Kk, int* splits, int* chunk);
+size_t gemm_dw_scratch_floats(int M, int Nn, int Kk);
+
+}  // namespace gib

@@ -1,0 +1,390 @@
+// fp32 SIMT GEMMs for the dense blocks of the hot path (edge-MLP, GRU, gather, APD readout).
+//
+// Why fp32 FMA and not plain TF32/BF16 tensor-core math: the parity bar is 1e-4 on the
+// logits and single-pass TF32 operand rounding alone gives 1.8e-2 (SURVEY.md §7 "hard
+// parts").  This file is the fp32-exact baseline path; the tcgen05 3xTF32 path
+// (gemm_tc.cu) replaces it where enabled and is validated against it.
+//
+// Layout contract (DESIGN.md "data layout"): every operand is row-major with a leading
+// dimension that is a multiple of 16 floats, pad columns hold exact zeros, the reduction
+// extent K is a multiple of 16.  Replaces the ATen `addmm`/`mm` call sites of
+// reference gnn/modules.py:162-170 (MLP), gnn/mpnn.py:296 (GRUCell) and their autograd.
+#include "gemm.cuh"
+
+namespace gib {
+
+constexpr int BK = 16;
+
+// ------------------------------------------------------------------------------------
+// C[M,N] = epilogue( A[M,K] * B[N,K]^T )       (both operands K-contiguous)
+// ------------------------------------------------------------------------------------
+template <int BM, int BN, int RM, int RN>
+__global__ void __launch_bounds__(256) sgemm_nt_kernel(const GemmNT p) {
+  static_assert((BM / (4 * RM)) * (BN / (4 * RN)) == 256, "256 threads");
+  __shared__ __align__(16) float As[2][BK][BM + 4];
+  __shared__ __align__(16) float Bs[2][BK][BN + 4];
+
+  const int tid = threadIdx.x;
+  const int w = tid >> 5, l = tid & 31;
+  const int ty = (w >> 1) * 4 + (l >> 3);  // 0..15 along M
+  const int tx = (w & 1) * 8 + (l & 7);    // 0..15 along N
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+
+  constexpr int LA = BM / 64, LB = BN / 64;  // float4 loads per thread per tile
+  float4 ra[LA], rb[LB];
+  const float* a_ptr[LA];
+  const float* b_ptr[LB];
+  bool a_ok[LA], b_ok[LB];
+#pragma unroll
+  for (int i = 0; i < LA; ++i) {
+    int q = tid + i * 256, row = q >> 2, kq = q & 3;
+    a_ok[i] = (m0 + row) < p.M;
+    a_ptr[i] = p.A + (size_t)(m0 + row) * p.lda + kq * 4;
+  }
+#pragma unroll
+  for (int i = 0; i < LB; ++i) {
+    int q = tid + i * 256, row = q >> 2, kq = q & 3;
+    b_ok[i] = (n0 + row) < p.N;
+    b_ptr[i] = p.B + (size_t)(n0 + row) * p.ldb + kq * 4;
+  }
+  auto gload = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < LA; ++i)
+      ra[i] = a_ok[i] ? __ldg(reinterpret_cast<const float4*>(a_ptr[i] + k0)) : make_float4(0, 0, 0, 0);
+#pragma unroll
+    for (int i = 0; i < LB; ++i)
+      rb[i] = b_ok[i] ? __ldg(reinterpret_cast<const float4*>(b_ptr[i] + k0)) : make_float4(0, 0, 0, 0);
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < LA; ++i) {
+      int q = tid + i * 256, row = q >> 2, kq = (q & 3) * 4;
+      As[buf][kq + 0][row] = ra[i].x; As[buf][kq + 1][row] = ra[i].y;
+      As[buf][kq + 2][row] = ra[i].z; As[buf][kq + 3][row] = ra[i].w;
+    }
+#pragma unroll
+    for (int i = 0; i < LB; ++i) {
+      int q = tid + i * 256, row = q >> 2, kq = (q & 3) * 4;
+      Bs[buf][kq + 0][row] = rb[i].x; Bs[buf][kq + 1][row] = rb[i].y;
+      Bs[buf][kq + 2][row] = rb[i].z; Bs[buf][kq + 3][row] = rb[i].w;
+    }
+  };
+
+  float acc[RM][4][RN][4];
+#pragma unroll
+  for (int a = 0; a < RM; ++a)
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int b = 0; b < RN; ++b)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[a][i][b][j] = 0.f;
+
+  const int ntiles = p.K / BK;
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  for (int t = 0; t < ntiles; ++t) {
+    const int buf = t & 1;
+    if (t + 1 < ntiles) gload((t + 1) * BK);
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float4 fa[RM], fb[RN];
+#pragma unroll
+      for (int a = 0; a < RM; ++a)
+        fa[a] = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4 + a * (BM / RM)]);
+#pragma unroll
+      for (int b = 0; b < RN; ++b)
+        fb[b] = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4 + b * (BN / RN)]);
+#pragma unroll
+      for (int a = 0; a < RM; ++a) {
+        const float av[4] = {fa[a].x, fa[a].y, fa[a].z, fa[a].w};
+#pragma unroll
+        for (int b = 0; b < RN; ++b) {
+          const float bv[4] = {fb[b].x, fb[b].y, fb[b].z, fb[b].w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[a][i][b][j] = fmaf(av[i], bv[j], acc[a][i][b][j]);
+        }
+      }
+    }
+    if (t + 1 < ntiles) sstore(buf ^ 1);
+    __syncthreads();
+  }
+
+  // ---- epilogue -------------------------------------------------------------------
+  const bool vec_c = (p.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+  const bool vec_x = p.aux && (p.ldaux & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.aux) & 15) == 0);
+#pragma unroll
+  for (int a = 0; a < RM; ++a)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = m0 + ty * 4 + a * (BM / RM) + i;
+      if (m >= p.M) continue;
+#pragma unroll
+      for (int b = 0; b < RN; ++b) {
+        const int n = n0 + tx * 4 + b * (BN / RN);
+        if (n >= p.n_store) continue;
+        float v[4] = {acc[a][i][b][0], acc[a][i][b][1], acc[a][i][b][2], acc[a][i][b][3]};
+        float x[4] = {0.f, 0.f, 0.f, 0.f};
+        if (p.mode != EPI_ACT) {
+          if (vec_x && n + 3 < p.n_store) {
+            float4 t4 = *reinterpret_cast<const float4*>(p.aux + (size_t)m * p.ldaux + n);
+            x[0] = t4.x; x[1] = t4.y; x[2] = t4.z; x[3] = t4.w;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (n + j < p.n_store) x[j] = p.aux[(size_t)m * p.ldaux + n + j];
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (p.mode == EPI_ACT) {
+            float bj = (p.bias && n + j < p.N) ? p.bias[n + j] : 0.f;
+            v[j] = act_f(v[j] + bj, p.act);
+          } else if (p.mode == EPI_MUL_DACT) {
+            v[j] = v[j] * dact_from_out(x[j], p.act);
+          } else {
+            v[j] = v[j] + x[j];
+          }
+          if (n + j >= p.n_valid) v[j] = 0.f;
+        }
+        float* dst = p.C + (size_t)m * p.ldc + n;
+        if (vec_c && n + 3 < p.n_store) {
+          *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (n + j < p.n_store) dst[j] = v[j];
+        }
+      }
+    }
+}
+
+int gemm_nt(const GemmNT& p, cudaStream_t st) {
+  if (p.M <= 0 || p.N <= 0) return 0;
+  if (p.K % BK != 0 || (p.lda & 3) || (p.ldb & 3) || p.K <= 0) {
+    set_error("gemm_nt: K=%d lda=%d ldb=%d violate the padded-layout contract", p.K, p.lda, p.ldb);
+    return -2;
+  }
+  ProfScope prof(PROF_GEMM_NT, p.work > 0 ? p.work : 2.0 * p.M * (double)p.N * p.K, st);
+  const long long ctas_big = (long long)ceil_div(p.M, 128) * ceil_div(p.N, 128);
+  if (ctas_big >= 148 && p.N > 64) {
+    dim3 grid(ceil_div(p.N, 128), ceil_div(p.M, 128));
+    sgemm_nt_kernel<128, 128, 2, 2><<<grid, 256, 0, st>>>(p);
+  } else if (p.N <= 64 && (long long)ceil_div(p.M, 128) >= 148) {
+    dim3 grid(ceil_div(p.N, 64), ceil_div(p.M, 128));
+    sgemm_nt_kernel<128, 64, 2, 1><<<grid, 256, 0, st>>>(p);
+  } else {
+    dim3 grid(ceil_div(p.N, 64), ceil_div(p.M, 64));
+    sgemm_nt_kernel<64, 64, 1, 1><<<grid, 256, 0, st>>>(p);
+  }
+  GIB_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------
+// dW partials:  P[z][n][k] = sum_{m in chunk z} G[m,n] * X[m,k]     (reduction over rows)
+// bias partials: Pb[z][n]  = sum_{m in chunk z} G[m,n]
+// ------------------------------------------------------------------------------------
+template <int BM, int BN, int RM, int RN>
+__global__ void __launch_bounds__(256) sgemm_tn_splitk_kernel(const GemmTN p) {
+  __shared__ __align__(16) float As[2][BK][BM + 4];
+  __shared__ __align__(16) float Bs[2][BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int w = tid >> 5, l = tid & 31;
+  const int ty = (w >> 1) * 4 + (l >> 3);
+  const int tx = (w & 1) * 8 + (l & 7);
+  const int n0 = blockIdx.y * BM;  // output row block (columns of G)
+  const int k0 = blockIdx.x * BN;  // output col block (columns of X)
+  const int z = blockIdx.z;
+  const int m_begin = z * p.chunk_rows;
+  const int m_end = min(p.M, m_begin + p.chunk_rows);
+
+  constexpr int LA = BM / 64, LB = BN / 64;
+  float4 ra[LA], rb[LB];
+  auto gload = [&](int m0) {
+#pragma unroll
+    for (int i = 0; i < LA; ++i) {
+      int q = tid + i * 256, kk = q / (BM / 4), c = (q % (BM / 4)) * 4;
+      bool ok = (m0 + kk) < m_end && (n0 + c) < p.Nn;
+      ra[i] = ok ? __ldg(reinterpret_cast<const float4*>(p.G + (size_t)(m0 + kk) * p.ldg + n0 + c))
+                 : make_float4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int i = 0; i < LB; ++i) {
+      int q = tid + i * 256, kk = q / (BN / 4), c = (q % (BN / 4)) * 4;
+      bool ok = (m0 + kk) < m_end && (k0 + c) < p.Kk;
+      rb[i] = ok ? __ldg(reinterpret_cast<const float4*>(p.X + (size_t)(m0 + kk) * p.ldx + k0 + c))
+                 : make_float4(0, 0, 0, 0);
+    }
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < LA; ++i) {
+      int q = tid + i * 256, kk = q / (BM / 4), c = (q % (BM / 4)) * 4;
+      *reinterpret_cast<float4*>(&As[buf][kk][c]) = ra[i];
+    }
+#pragma unroll
+    for (int i = 0; i < LB; ++i) {
+      int q = tid + i * 256, kk = q / (BN / 4), c = (q % (BN / 4)) * 4;
+      *reinterpret_cast<float4*>(&Bs[buf][kk][c]) = rb[i];
+    }
+  };
+
+  float acc[RM][4][RN][4];
+  float bacc[RM][4];
+#pragma unroll
+  for (int a = 0; a < RM; ++a)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      bacc[a][i] = 0.f;
+#pragma unroll
+      for (int b = 0; b < RN; ++b)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[a][i][b][j] = 0.f;
+    }
+  const bool do_bias = p.ws_bias != nullptr && blockIdx.x == 0 && (w & 1) == 0;  // warp-uniform
+
+  const int ntiles = (m_end > m_begin) ? ceil_div(m_end - m_begin, BK) : 0;
+  if (ntiles > 0) {
+    gload(m_begin);
+    sstore(0);
+  }
+  __syncthreads();
+  for (int t = 0; t < ntiles; ++t) {
+    const int buf = t & 1;
+    if (t + 1 < ntiles) gload(m_begin + (t + 1) * BK);
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float4 fa[RM], fb[RN];
+#pragma unroll
+      for (int a = 0; a < RM; ++a)
+        fa[a] = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4 + a * (BM / RM)]);
+#pragma unroll
+      for (int b = 0; b < RN; ++b)
+        fb[b] = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4 + b * (BN / RN)]);
+#pragma unroll
+      for (int a = 0; a < RM; ++a) {
+        const float av[4] = {fa[a].x, fa[a].y, fa[a].z, fa[a].w};
+        if (do_bias) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) bacc[a][i] += av[i];
+        }
+#pragma unroll
+        for (int b = 0; b < RN; ++b) {
+          const float bv[4] = {fb[b].x, fb[b].y, fb[b].z, fb[b].w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[a][i][b][j] = fmaf(av[i], bv[j], acc[a][i][b][j]);
+        }
+      }
+    }
+    if (t + 1 < ntiles) sstore(buf ^ 1);
+    __syncthreads();
+  }
+
+  float* out = p.ws + (size_t)z * p.Nn * p.Kk;
+#pragma unroll
+  for (int a = 0; a < RM; ++a)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int n = n0 + ty * 4 + a * (BM / RM) + i;
+      if (n >= p.Nn) continue;
+#pragma unroll
+      for (int b = 0; b < RN; ++b) {
+        const int k = k0 + tx * 4 + b * (BN / RN);
+        if (k >= p.Kk) continue;
+        *reinterpret_cast<float4*>(out + (size_t)n * p.Kk + k) =
+            make_float4(acc[a][i][b][0], acc[a][i][b][1], acc[a][i][b][2], acc[a][i][b][3]);
+      }
+      if (do_bias && (l & 7) == 0) p.ws_bias[(size_t)z * p.Nn + n] = bacc[a][i];
+    }
+}
+
+// out[(r)*rs + c*cs] (+)= sum_z ws[z][prow(r)][c]   with prow(r) = (r / Rb) * Rbp + r % Rb
+__global__ void reduce_dw_kernel(const float* __restrict__ ws, int splits, int Nn, int Kk,
+                                 float* __restrict__ out, int R, int C, int Rb, int Rbp,
+                                 long long rs, long long cs) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)R * C) return;
+  const int r = (int)(idx / C), c = (int)(idx % C);
+  const int prow = (r / Rb) * Rbp + (r % Rb);
+  const float* src = ws + (size_t)prow * Kk + c;
+  const size_t stride = (size_t)Nn * Kk;
+  float s = 0.f;
+  for (int zi = 0; zi < splits; ++zi) s += src[zi * stride];
+  out[r * rs + c * cs] += s;
+}
+
+__global__ void reduce_db_kernel(const float* __restrict__ wsb, int splits, int Nn,
+                                 float* __restrict__ out, int R, int Rb, int Rbp) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const int prow = (r / Rb) * Rbp + (r % Rb);
+  float s = 0.f;
+  for (int zi = 0; zi < splits; ++zi) s += wsb[(size_t)zi * Nn + prow];
+  out[r] += s;
+}
+
+size_t gemm_dw_scratch_floats(int M, int Nn, int Kk) {
+  int splits, chunk;
+  gemm_dw_plan(M, Nn, Kk, &splits, &chunk);
+  return (size_t)splits * Nn * Kk + (size_t)splits * Nn;
+}
+
+void gemm_dw_plan(int M, int Nn, int Kk, int* splits, int* chunk) {
+  const int tiles = ceil_div(Nn, 128) * ceil_div(Kk, 128);
+  int s = ceil_div(2 * 148, tiles);
+  const int max_s = ceil_div(M, 64) > 0 ? ceil_div(M, 64) : 1;  // >= 64 rows per split
+  if (s > max_s) s = max_s;
+  if (s < 1) s = 1;
+  int c = ceil_div(ceil_div(M, s), BK) * BK;
+  if (c < BK) c = BK;
+  s = ceil_div(M, c);
+  if (s < 1) s = 1;
+  *splits = s;
+  *chunk = c;
+}
+
+int gemm_dw(const GemmDW& q, cudaStream_t st) {
+  if (q.M <= 0) return 0;  // nothing to add
+  if ((q.ldg & 3) || (q.ldx & 3) || (q.Nn & 3) || (q.Kk & 3)) {
+    set_error("gemm_dw: ldg=%d ldx=%d Nn=%d Kk=%d violate the padded-layout contract", q.ldg, q.ldx, q.Nn, q.Kk);
+    return -2;
+  }
+  ProfScope prof(PROF_GEMM_DW, q.work > 0 ? q.work : 2.0 * q.M * (double)q.R * q.C, st);
+  int splits, chunk;
+  gemm_dw_plan(q.M, q.Nn, q.Kk, &splits, &chunk);
+  GemmTN p;
+  p.G = q.G; p.ldg = q.ldg; p.X = q.X; p.ldx = q.ldx; p.M = q.M; p.Nn = q.Nn; p.Kk = q.Kk;
+  p.chunk_rows = chunk;
+  p.ws = q.scratch;
+  p.ws_bias = q.dbias ? q.scratch + (size_t)splits * q.Nn * q.Kk : nullptr;
+  if (q.dW) {
+    dim3 grid(ceil_div(q.Kk, 128), ceil_div(q.Nn, 128), splits);
+    sgemm_tn_splitk_kernel<128, 128, 2, 2><<<grid, 256, 0, st>>>(p);
+    GIB_LAUNCH_CHECK();
+    const long long tot = (long long)q.R * q.C;
+    reduce_dw_kernel<<<(unsigned)ceil_div_ll(tot, 256), 256, 0, st>>>(p.ws, splits, q.Nn, q.Kk, q.dW, q.R, q.C,
+                                                                     q.Rb, q.Rbp, q.rs, q.cs);
+    GIB_LAUNCH_CHECK();
+  }
+  if (q.dbias) {
+    if (!q.dW) {  // bias only: run one k-tile column
+      GemmTN pb = p;
+      pb.Kk = 4;  // minimal X extent; acc discarded
+      dim3 grid(1, ceil_div(q.Nn, 128), splits);
+      // ws slab must still hold Nn*4 floats per split: it does (Kk >= 16 in every caller)
+      sgemm_tn_splitk_kernel<128, 128, 2, 2><<<grid, 256, 0, st>>>(pb);
+      GIB_LAUNCH_CHECK();
+    }
+    reduce_db_kernel<<<ceil_div(q.R, 256), 256, 0, st>>>(p.ws_bias, splits, q.Nn, q.dbias, q.R, q.Rb, q.Rbp);
+    GIB_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+}  // namespace gib

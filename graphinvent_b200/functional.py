@@ -1,0 +1,203 @@
+"""
+Host-side glue between the drop-in modules and the C-ABI: one `torch.autograd.Function` whose
+forward/backward are `gib_model_forward` / `gib_model_backward`, plus the fused loss.
+
+PyTorch is used for device memory (caching allocator), streams and autograd plumbing only.
+No computation of the hot path happens in ATen, and there is no CPU path: CPU tensors raise.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from ._lib import Dims, HDR_E, HDR_FLAGS, HDR_INTS, HDR_P, MODEL_ID, check, lib
+
+_u8 = torch.uint8
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def make_dims(model, batch):
+    d = Dims()
+    kw = model.dims()
+    for name, _ in Dims._fields_:
+        if name in ("model", "B", "big"):
+            continue
+        setattr(d, name, int(kw.get(name, 0)))
+    d.model = MODEL_ID[kw["model"]]
+    d.B = int(batch)
+    d.big = float(kw.get("big", 1e6))
+    return d
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if not t.is_cuda:
+            raise RuntimeError(
+                "graphinvent_b200 runs only on CUDA tensors (sm_100a kernels); there is no CPU fallback. "
+                "Move the model and the batch to the GPU.")
+
+
+def _check_params(model, d, params):
+    n = lib.gib_model_num_params(ctypes.byref(d))
+    if n != len(params):
+        raise RuntimeError(f"parameter table mismatch: library expects {n} tensors, module has {len(params)}")
+    for i, p in enumerate(params):
+        want = lib.gib_model_param_numel(ctypes.byref(d), i)
+        if want != p.numel():
+            raise RuntimeError(f"parameter {i} has {p.numel()} elements, library expects {want}")
+        if p.dtype != torch.float32 or not p.is_contiguous():
+            raise RuntimeError("parameters must be contiguous float32")
+
+
+def _ptr_table(tensors):
+    arr = (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+    return arr
+
+
+def packed_weights(model, d, params):
+    """Zero-padded / transposed weight arena, rebuilt only when a parameter changed
+    (keyed on data_ptr + in-place version counter, so generation re-uses it every round)."""
+    key = tuple((p.data_ptr(), p._version) for p in params)
+    if model._packed is not None and model._packed_key == key:
+        return model._packed
+    if model._packed_key is None or len(model._packed_key) != len(key):
+        _check_params(model, d, params)
+    dev = params[0].device
+    nbytes = lib.gib_model_packed_bytes(ctypes.byref(d))
+    packed = torch.empty(nbytes, dtype=_u8, device=dev)
+    check(lib.gib_model_pack(ctypes.byref(d), _ptr_table(params), _ptr(packed), _stream(dev)), "gib_model_pack")
+    model._packed, model._packed_key = packed, key
+    return packed
+
+
+class GraphBatch:
+    """Device-side bond-entry lists + CSR of one batch (output of K0) and its host header."""
+    __slots__ = ("hdr", "hdr_np", "buf", "n_entries", "n_rows", "flags")
+
+    def __init__(self, d, edges):
+        dev = edges.device
+        st = _stream(dev)
+        cws = torch.empty(lib.gib_graph_count_ws_bytes(ctypes.byref(d)), dtype=_u8, device=dev)
+        check(lib.gib_graph_count(ctypes.byref(d), _ptr(edges), _ptr(cws), st), "gib_graph_count")
+        # the single device->host read of a forward: 16 ints (the reference syncs twice in nonzero())
+        self.hdr_np = cws[: HDR_INTS * 4].view(torch.int32).cpu().numpy().copy()
+        self.hdr = self.hdr_np.ctypes.data_as(ctypes.c_void_p)
+        self.n_entries = int(self.hdr_np[HDR_E])
+        self.n_rows = int(self.hdr_np[HDR_P])
+        self.flags = int(self.hdr_np[HDR_FLAGS])
+        self.buf = torch.empty(max(256, lib.gib_graph_bytes(ctypes.byref(d), self.hdr)), dtype=_u8, device=dev)
+        check(lib.gib_graph_fill(ctypes.byref(d), _ptr(edges), _ptr(cws), self.hdr, _ptr(self.buf), st),
+              "gib_graph_fill")
+
+    def array(self, d, which, count, dtype=torch.int32):
+        """view of one internal array (tests): which = 0 ent_src .. 6 src_ent (include/gib200.h)"""
+        addr = lib.gib_graph_array(ctypes.byref(d), self.hdr, _ptr(self.buf), which)
+        off = addr - self.buf.data_ptr()
+        return self.buf[off: off + count * 4].view(dtype)
+
+
+class _MPNNFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, nodes, edges, *params):
+        dev = nodes.device
+        B = nodes.shape[0]
+        d = make_dims(model, B)
+        st = _stream(dev)
+        graph = GraphBatch(d, edges)
+        packed = packed_weights(model, d, params)
+        ws_bytes = lib.gib_model_workspace_bytes(ctypes.byref(d), graph.hdr)
+        if ws_bytes == 0:
+            check(-1, "gib_model_workspace_bytes")
+        ws = torch.empty(ws_bytes, dtype=_u8, device=dev)
+        apd = d.N * d.f_add + d.N * d.f_conn + 1
+        out = torch.empty(B, apd, dtype=torch.float32, device=dev)
+        check(lib.gib_model_forward(ctypes.byref(d), graph.hdr, _ptr(nodes), _ptr(edges), _ptr(graph.buf),
+                                    _ptr(packed), _ptr(ws), _ptr(out), st), "gib_model_forward")
+        model.last_stats = {"entries": graph.n_entries, "rows": graph.n_rows, "workspace_bytes": ws_bytes,
+                            "flags": graph.flags}
+        ctx.model, ctx.d, ctx.graph = model, d, graph
+        ctx.save_for_backward(nodes, edges, packed, ws, out)
+        ctx.param_meta = [(p.shape, p.numel()) for p in params]
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        nodes, edges, packed, ws, out = ctx.saved_tensors
+        d, graph, model = ctx.d, ctx.graph, ctx.model
+        dev = nodes.device
+        dout = dout.contiguous().float()
+        total = sum(n for _, n in ctx.param_meta)
+        flat = torch.zeros(total, dtype=torch.float32, device=dev)   # one bucket: grads are views of it
+        views, o = [], 0
+        for shape, n in ctx.param_meta:
+            views.append(flat[o:o + n].view(shape))
+            o += n
+        scratch = torch.empty(lib.gib_model_bwd_scratch_bytes(ctypes.byref(d), graph.hdr), dtype=_u8, device=dev)
+        check(lib.gib_model_backward(ctypes.byref(d), graph.hdr, _ptr(nodes), _ptr(edges), _ptr(graph.buf),
+                                     _ptr(packed), _ptr(ws), _ptr(out), _ptr(dout), _ptr_table(views),
+                                     _ptr(scratch), _stream(dev)), "gib_model_backward")
+        if model._grad_hook is not None:
+            model._grad_hook(flat)      # e.g. the single NCCL all-reduce of data-parallel training
+        return (None, None, None, *views)
+
+
+def mpnn_forward(model, nodes, edges):
+    _require_cuda(nodes, edges)
+    params = list(model.parameters())
+    _require_cuda(*params)
+    if nodes.dim() != 3 or edges.dim() != 4:
+        raise ValueError("expected nodes [B,N,F] and edges [B,N,N,Ef]")
+    nodes = nodes.contiguous().float()
+    edges = edges.contiguous().float()
+    if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+        return _MPNNFunction.apply(model, nodes, edges, *params)
+    with torch.no_grad():
+        return _MPNNFunction.apply(model, nodes, edges, *[p.detach() for p in params])
+
+
+# ------------------------------------------------------------------------------------------
+# Workflow.loss (Workflow.py:833-860): KLDivLoss(batchmean)(log_softmax(output), target/sum)
+# ------------------------------------------------------------------------------------------
+class _KLLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, output, target):
+        B, apd = output.shape
+        rows = torch.empty(B, dtype=torch.float32, device=output.device)
+        dout = torch.empty_like(output)
+        check(lib.gib_kl_loss_fwd_bwd(_ptr(output), _ptr(target), B, apd, 1.0 / B, _ptr(rows), _ptr(dout),
+                                      _stream(output.device)), "gib_kl_loss_fwd_bwd")
+        ctx.save_for_backward(dout)
+        return rows.sum() / B
+
+    @staticmethod
+    def backward(ctx, g):
+        (dout,) = ctx.saved_tensors
+        return dout * g, None
+
+
+def kl_loss(output, target):
+    """Fused `Workflow.loss`: returns the scalar batch-mean KL divergence; its backward is the
+    closed form (softmax(output) - target_hat) / B computed in the same kernel."""
+    _require_cuda(output, target)
+    return _KLLoss.apply(output.contiguous().float(), target.contiguous().float())
+
+
+def sample_actions(output, uniforms=None, generator=None):
+    """softmax + one categorical draw per molecule from APD logits (GraphGenerator.py:121,535-542),
+    inverse-CDF on uniforms in [0,1).  Returns (flat action index int32 [B], likelihood [B])."""
+    _require_cuda(output)
+    B, apd = output.shape
+    if uniforms is None:
+        uniforms = torch.rand(B, device=output.device, generator=generator)
+    action = torch.empty(B, dtype=torch.int32, device=output.device)
+    lik = torch.empty(B, dtype=torch.float32, device=output.device)
+    check(lib.gib_sample_actions(_ptr(output.contiguous()), B, apd, _ptr(uniforms.contiguous().float()),
+                                 _ptr(action), _ptr(lik), _stream(output.device)), "gib_sample_actions")
+    return action, lik

@@ -1,0 +1,147 @@
+/*
+ * gib200 -- C-ABI of the B200-native GraphINVENT MPNN hot path (libgib200.so).
+ *
+ * The reference has no FFI layer: its boundary for this path is the Python
+ * `torch.nn.Module` protocol (`gnn.mpnn.{MNN,GGNN,AttentionGGNN,EMN}(constants)`,
+ * `forward(nodes, edges) -> logits`).  The drop-in modules in
+ * `graphinvent_b200/gnn/` keep that protocol and bind the entry points below through
+ * ctypes (INTEGRATION.md shows the stub).  Each entry point names the reference code
+ * it replaces (paths relative to /root/reference/graphinvent/).
+ *
+ * Conventions
+ *  - every pointer except `hdr_host`, `params` / `grads` (host arrays of device pointers)
+ *    and `dims` is a DEVICE pointer owned by the caller (PyTorch caching allocator:
+ *    `tensor.data_ptr()`); the library never allocates or frees device memory -- sizes come
+ *    from the *_bytes() queries;
+ *  - `stream` is a cudaStream_t (`torch.cuda.current_stream().cuda_stream`); every call is
+ *    asynchronous on it and performs no host synchronisation;
+ *  - return value: 0 ok, < 0 invalid argument (see gib_last_error()), > 0 a cudaError_t;
+ *  - nothing is thrown across the boundary; no global mutable state besides the
+ *    thread-local error string;
+ *  - all reductions run in a fixed order (no float atomics): results are bit-stable.
+ *
+ * Tensor layouts (reference `BlockDatasetLoader.py:135-143`):
+ *    nodes  float32 [B, N, F]        dense, zero padded
+ *    edges  float32 [B, N, N, Ef]    dense, zero padded, dst = row i, src = column j
+ *    out    float32 [B, N*f_add + N*f_conn + 1]   un-normalised (SELU-activated) APD logits
+ */
+#ifndef GIB200_H
+#define GIB200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* gib_stream; /* cudaStream_t */
+
+enum { GIB_GGNN = 0, GIB_MNN = 1, GIB_ATTGGNN = 2, GIB_EMN = 3 };
+
+/* Hyper-parameters the reference reads from `constants`. */
+typedef struct gib_dims {
+  int model;                       /* GIB_* */
+  int B, N, F, Ef;                 /* batch, max_n_nodes, n_node_features, n_edge_features */
+  int H, M, T;                     /* hidden_node_features, message_size, message_passes
+                                      (EMN: H = M = edge_emb_size) */
+  int msg_hidden, msg_depth;       /* GGNN: enn_*;  AttGGNN / EMN: msg_* */
+  int att_hidden, att_depth;       /* AttGGNN / EMN: att_* */
+  int eemb_hidden, eemb_depth;     /* EMN: edge_emb_* */
+  int gather_width, gatt_hidden, gatt_depth, gemb_hidden, gemb_depth;
+  int mlp1_hidden, mlp1_depth, mlp2_hidden, mlp2_depth;
+  int f_add, f_conn;               /* len_f_add_per_node, len_f_conn_per_node */
+  float big;                       /* constants.big_positive (1e6) */
+} gib_dims;
+
+/* Graph header: 16 ints written on the device by gib_graph_count() at the start of its
+ * workspace; the caller copies them to the host (the one D2H read of a forward) and passes
+ * them back as `hdr_host`.  Index meaning: */
+enum {
+  GIB_HDR_E = 0,          /* bond entries (non-zero elements of `edges`) */
+  GIB_HDR_P = 1,          /* rows of the type-grouped entry arrays (groups padded to 128) */
+  GIB_HDR_TYPE_COUNT = 2, /* [4] */
+  GIB_HDR_TYPE_BASE = 6,  /* [5] */
+  GIB_HDR_FLAGS = 11,     /* bit0: a bond with >1 non-zero type; bit1: a bond value != 1 */
+  GIB_HDR_INTS = 16
+};
+
+const char* gib_last_error(void);
+int gib_version(void);
+
+/* ---- K0: edges -> bond entries + CSR.  Replaces summation_mpnn.py:102-118,
+ *      aggregation_mpnn.py:105-148, edge_mpnn.py:104-173. ------------------------------- */
+size_t gib_graph_count_ws_bytes(const gib_dims* d);
+int gib_graph_count(const gib_dims* d, const float* edges, void* count_ws, gib_stream stream);
+size_t gib_graph_bytes(const gib_dims* d, const int* hdr_host);
+int gib_graph_fill(const gib_dims* d, const float* edges, const void* count_ws, const int* hdr_host,
+                   void* graph_buf, gib_stream stream);
+/* device addresses of the arrays inside graph_buf, for tests / standalone kernel calls:
+ * which = 0 ent_src, 1 ent_dst, 2 ent_w, 3 dst_ptr, 4 dst_ent, 5 src_ptr, 6 src_ent */
+void* gib_graph_array(const gib_dims* d, const int* hdr_host, void* graph_buf, int which);
+
+/* ---- parameters: state_dict order of the reference ------------- */
+int gib_model_num_params(const gib_dims* d);
+long long gib_model_param_numel(const gib_dims* d, int index);
+size_t gib_model_packed_bytes(const gib_dims* d);
+/* zero-padded + transposed copies of every weight (and 3xTF32 splits when enabled) */
+int gib_model_pack(const gib_dims* d, const float* const* params, void* packed, gib_stream stream);
+
+/* ---- whole-model forward / backward.  Replaces SummationMPNN.forward
+ *      (summation_mpnn.py:80-149), AggregationMPNN.forward (aggregation_mpnn.py:83-168),
+ *      EdgeMPNN.forward (edge_mpnn.py:82-192), the model bodies in mpnn.py and
+ *      GraphGather / GlobalReadout (modules.py:39-52, 237-281), and their autograd. ------- */
+size_t gib_model_workspace_bytes(const gib_dims* d, const int* hdr_host);
+int gib_model_forward(const gib_dims* d, const int* hdr_host, const float* nodes, const float* edges,
+                      const void* graph_buf, const void* packed, void* workspace, float* out,
+                      gib_stream stream);
+size_t gib_model_bwd_scratch_bytes(const gib_dims* d, const int* hdr_host);
+/* grads[i] (same order / shapes as params) are ACCUMULATED into (+=). */
+int gib_model_backward(const gib_dims* d, const int* hdr_host, const float* nodes, const float* edges,
+                       const void* graph_buf, const void* packed, const void* workspace,
+                       const float* out, const float* dout, float* const* grads, void* scratch,
+                       gib_stream stream);
+
+/* ---- call-site post-ops (Workflow.py:833-860): KLDivLoss(batchmean)(log_softmax(out),
+ *      target / sum(target)) and its gradient w.r.t. `out`, one kernel.
+ *      loss_rows[b] = per-molecule KL (sum and divide by B on the caller side or pass
+ *      inv_scale); dout = (softmax(out) - t_hat) * grad_scale. ---------------------------- */
+int gib_kl_loss_fwd_bwd(const float* out, const float* target, int B, int apd, float grad_scale,
+                        float* loss_rows, float* dout, gib_stream stream);
+
+/* ---- single kernels (unit tests, ncu evidence, reuse) --------------------------------- */
+/* Y = act(X W^T + b); X [M, ldx], W packed [Np, Kp] (ldw), Y [M, ldy]; act 0 none / 1 selu / 2 tanh */
+int gib_linear_fwd(const float* X, int ldx, const float* W, int ldw, const float* bias, float* Y, int ldy,
+                   int M, int N, int K, int act, gib_stream stream);
+/* dW[R,C] += G^T X, dbias[R] += colsum(G); G [M, ldg], X [M, ldx]; scratch from gib_dw_scratch_bytes */
+size_t gib_dw_scratch_bytes(int M, int Nn, int Kk);
+int gib_linear_bwd_dw(const float* G, int ldg, int Nn, const float* X, int ldx, int Kk, int M, float* dW,
+                      float* dbias, int R, int C, void* scratch, gib_stream stream);
+/* K2 scatter-aggregate: out[s,:] = sum_{q in [ptr[s],ptr[s+1])} w[ent[q]] * msg[ent[q],:]   (w may be NULL) */
+int gib_scatter_sum(float* out, const float* msg, int ld, const int* ptr, const int* ent, const float* w,
+                    long long S, gib_stream stream);
+/* K2' segmented softmax-aggregate (AttentionGGNN) */
+int gib_seg_softmax(float* out, const float* EM, const float* EN, int ld, const int* ptr, const int* ent,
+                    const float* w, long long S, gib_stream stream);
+/* GRU gates: hn = GRU(gi, gh, h) on rows whose CSR segment is non-empty (ptr may be NULL) */
+int gib_gru_gates(float* hn, const float* gi, const float* gh, const float* h, int Hp, const int* ptr,
+                  long long S, gib_stream stream);
+/* GraphGather softmax readout */
+int gib_graph_gather(float* g, float* att, const float* en, const float* em, int ld, const int* ptr, int N,
+                     int B, float big, gib_stream stream);
+
+/* ---- generation round post-processing: softmax + categorical sample of one
+ *      action per molecule from the APD logits, inverse-CDF on a caller-provided uniform. ---- */
+int gib_sample_actions(const float* out, int B, int apd, const float* uniforms, int* action,
+                       float* likelihood, gib_stream stream);
+
+/* ---- measurement hooks: CUDA-event timing per kernel class on the launching stream.
+ *      class 0 = forward/dX GEMMs, 1 = dW GEMMs (+ split-K reduce), 2 = scatter-aggregate (K2).
+ *      work = algorithmic FLOPs (classes 0,1) or bytes (class 2).  Collect after a stream sync. -- */
+void gib_profile_enable(int on);
+long long gib_launch_count(void); /* kernels launched by this library since load */
+int gib_profile_collect(double* ms, double* work, long long* count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GIB200_H */

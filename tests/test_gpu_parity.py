@@ -1,0 +1,216 @@
+"""GPU: the drop-in modules (CUDA path through the C-ABI) against the oracle and the golden
+fixtures of the unmodified reference.  Tolerances (north_star / SURVEY.md §8c):
+   logits  max-abs <= 1e-4 vs CPU fp32, APD argmax identical,
+   grads   per-tensor max|d| / max|g| <= 1e-4,
+   loss    <= 1e-5."""
+import copy
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+import torch
+
+from tests.conftest import MODELS, load_gdb13, load_small, pretrained_path
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_TOL = 1e-4
+GRAD_REL_TOL = 1e-4
+
+
+def _build(C, sd=None):
+    from graphinvent_b200.gnn import mpnn
+    net = mpnn.create(C)
+    if sd is not None:
+        net.load_state_dict(sd)
+    return net.cuda()
+
+
+def _step(net, nodes, edges, target):
+    from graphinvent_b200 import functional as Fn
+    net.zero_grad()
+    out = net(nodes.cuda(), edges.cuda())
+    loss = Fn.kl_loss(out, target.cuda())
+    loss.backward()
+    grads = OrderedDict((k, p.grad.detach().cpu()) for k, p in net.named_parameters())
+    return out.detach().cpu(), float(loss), grads
+
+
+def _assert_grads(got, want):
+    worst = ("", 0.0)
+    for k, g in want.items():
+        scale = max(g.abs().max().item(), 1e-8)
+        rel = (got[k] - g).abs().max().item() / scale
+        if rel > worst[1]:
+            worst = (k, rel)
+    assert worst[1] <= GRAD_REL_TOL, f"worst gradient {worst[0]}: rel err {worst[1]:.3e}"
+
+
+@pytest.mark.parametrize("model", MODELS)
+def test_golden_small_forward_backward(model):
+    """fixture = unmodified reference on CPU (tests/golden/make_golden.py); includes the generator's corner
+    graphs: dummy self-loop graph, empty graph, isolated atom, degree-5 atom."""
+    fx = load_small(model)
+    net = _build(fx["C"], fx["sd"])
+    assert list(net.state_dict().keys()) == list(fx["sd"].keys())
+    out, loss, grads = _step(net, fx["nodes"], fx["edges"], fx["target"])
+    assert torch.isfinite(out).all()
+    assert (out - fx["logits"]).abs().max().item() <= LOGIT_TOL
+    assert torch.equal(out.argmax(1), fx["logits"].argmax(1))
+    assert abs(loss - fx["loss"]) <= 1e-5
+    _assert_grads(grads, fx["grads"])
+
+
+@pytest.mark.parametrize("model", MODELS)
+def test_default_dims_vs_oracle(model):
+    """reference default hyper-parameters (defaults.py:145-433), gdb13 chemistry, real-data-like sizes"""
+    from graphinvent_b200 import synthetic as S
+    from oracle import mpnn_oracle as O
+    C = O.make_constants(model)
+    sd = O.init_state_dict(C, seed=11)
+    n, e = S.random_graphs(96, 13, 5, 3, seed=12, min_atoms=0)
+    n2, e2 = S.corner_case_graphs(13, 8)
+    nodes = torch.from_numpy(np.concatenate([n2, n])).float()
+    edges = torch.from_numpy(np.concatenate([e2, e])).float()
+    target = torch.from_numpy(S.random_targets(nodes.shape[0], 625, seed=3))
+    loss_ref, out_ref, g_ref = O.train_step_grads(sd, C, nodes, edges, target)
+    net = _build(C, sd)
+    out, loss, grads = _step(net, nodes, edges, target)
+    assert (out - out_ref).abs().max().item() <= LOGIT_TOL
+    assert torch.equal(out.argmax(1), out_ref.argmax(1))
+    assert abs(loss - float(loss_ref)) <= 1e-5
+    _assert_grads(grads, g_ref)
+
+
+def test_pretrained_checkpoint_on_real_gdb13_rows():
+    """known-answer weights (reference data/fine-tuning/gdb13_1K-debug/pretrained_model.pth) x the first 256
+    real rows of gdb13_1K/train.h5; golden logits / loss / gradient statistics from the unmodified reference."""
+    path = pretrained_path()
+    if path is None:
+        pytest.skip("tests/golden/_local/pretrained_model.pth absent")
+    from oracle import mpnn_oracle as O
+    fx = load_gdb13()
+    sd = torch.load(path, map_location="cpu", weights_only=False)
+    net = _build(O.make_constants("GGNN"), sd)            # reference .pth loads unchanged
+    out, loss, grads = _step(net, fx["nodes"], fx["edges"], fx["apds"])
+    assert (out - fx["logits"]).abs().max().item() <= LOGIT_TOL
+    assert torch.equal(out.argmax(1), fx["logits"].argmax(1))
+    assert abs(loss - fx["loss"]) <= 2e-5
+    g = fx["g"]
+    names = [str(s) for s in g["grad_names"]]
+    for k, amax, gsum in zip(names, g["grad_absmax"], g["grad_sum"]):
+        assert abs(grads[k].abs().max().item() - float(amax)) <= 1e-4 * max(float(amax), 1e-6) + 1e-9, k
+    for k in g.files:
+        if k.startswith("grad/"):
+            want = torch.from_numpy(g[k])
+            scale = max(want.abs().max().item(), 1e-8)
+            assert (grads[k[5:]] - want).abs().max().item() / scale <= GRAD_REL_TOL, k
+
+
+def test_bond_values_other_than_one_and_multi_type_bonds():
+    """GGNN / MNN follow the reference arithmetic for arbitrary non-negative bond values
+    (mpnn.py:284-294: value * MLP_t(value * h)); AttentionGGNN refuses multi-type bonds loudly."""
+    from oracle import mpnn_oracle as O
+    for model in ("GGNN", "MNN"):
+        fx = load_small(model)
+        edges = fx["edges"].clone()
+        edges[6, 0, 1, :] = torch.tensor([0.5, 0.0, 2.0]); edges[6, 1, 0, :] = torch.tensor([0.5, 0.0, 2.0])
+        edges[7] *= 1.5
+        out_ref = O.forward(fx["sd"], fx["C"], fx["nodes"], edges)
+        net = _build(fx["C"], fx["sd"])
+        with torch.no_grad():
+            out = net(fx["nodes"].cuda(), edges.cuda()).cpu()
+        assert (out - out_ref).abs().max().item() <= LOGIT_TOL, model
+    fx = load_small("AttGGNN")
+    edges = fx["edges"].clone()
+    edges[6, 0, 1, :] = 1.0
+    with pytest.raises(RuntimeError, match="one bond type"):
+        _build(fx["C"], fx["sd"])(fx["nodes"].cuda(), edges.cuda())
+
+
+def test_module_protocol_eval_nograd_deepcopy_statedict_reentrancy():
+    """what Workflow / GraphGenerator / the RL loop do with the module."""
+    from graphinvent_b200 import functional as Fn
+    fx = load_small("GGNN")
+    net = _build(fx["C"], fx["sd"])
+    nodes, edges, tgt = fx["nodes"].cuda(), fx["edges"].cuda(), fx["target"].cuda()
+    net.eval()
+    with torch.no_grad():
+        o1 = net(nodes, edges)
+    net.train()
+    o2 = net(nodes, edges)
+    assert torch.equal(o1, o2)                                   # p = 0 dropout: identical; bit-stable kernels
+    twin = copy.deepcopy(net)                                    # Workflow.py:187-188
+    assert torch.equal(twin(nodes, edges), o2)
+    sd = net.state_dict()
+    assert all(torch.equal(sd[k].cpu(), fx["sd"][k]) for k in fx["sd"])
+    # RL-style: several forwards, one backward (Workflow.py:582-598)
+    net.zero_grad()
+    l1 = Fn.kl_loss(net(nodes[:16], edges[:16]), tgt[:16])
+    l2 = Fn.kl_loss(net(nodes[16:], edges[16:]), tgt[16:])
+    (l1 * 16 + l2 * 16).div(32).backward()
+    g_two = [p.grad.clone() for p in net.parameters()]
+    net.zero_grad()
+    Fn.kl_loss(net(nodes, edges), tgt).backward()
+    for a, b in zip(g_two, net.parameters()):
+        assert (a - b.grad).abs().max().item() <= 1e-5 * max(1.0, b.grad.abs().max().item())
+    # optimizer step changes the weights -> packed copy must refresh
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    opt.step()
+    o3 = net(nodes, edges)
+    assert not torch.equal(o3, o2)
+    # varying batch size (last batch, generation)
+    assert net(nodes[:1], edges[:1]).shape == (1, o2.shape[1])
+    assert (net(nodes[:3], edges[:3]) - o3[:3]).abs().max().item() == 0.0
+
+
+def test_cpu_tensors_fail_loudly():
+    fx = load_small("GGNN")
+    from graphinvent_b200.gnn import mpnn
+    net = mpnn.create(fx["C"])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net(fx["nodes"], fx["edges"])
+
+
+@pytest.mark.parametrize("cfg", ["C2", "C4_slice"])
+def test_full_size_properties(cfg):
+    """BASELINE.json sizes, where the CPU oracle is too slow to be the checker: size-independent
+    properties of the path -- (1) molecules are independent, so any sub-batch reproduces its rows
+    bit-exactly; (2) permuting the batch permutes the logits; (3) gradients are additive over a
+    partition of the batch; (4) one oracle-checked slice."""
+    from graphinvent_b200 import functional as Fn
+    from graphinvent_b200 import synthetic as S
+    from oracle import mpnn_oracle as O
+    if cfg == "C2":
+        C = O.make_constants("GGNN", hidden_node_features=128, message_size=128, message_passes=4)
+        B, N, na, nc = 1024, 13, 5, 3
+    else:
+        C = O.make_constants("GGNN", max_n_nodes=38, n_node_features=12, len_f_add_per_node=81)
+        B, N, na, nc = 512, 38, 9, 3
+    apd = N * (C.len_f_add_per_node + C.len_f_conn_per_node) + 1
+    sd = O.init_state_dict(C, seed=0)
+    n, e = S.random_graphs(B, N, na, nc, seed=1002)
+    nodes, edges = torch.from_numpy(n).float().cuda(), torch.from_numpy(e).float().cuda()
+    target = torch.from_numpy(S.random_targets(B, apd, seed=2)).cuda()
+    net = _build(C, sd)
+    with torch.no_grad():
+        full = net(nodes, edges)
+        half = net(nodes[B // 2:], edges[B // 2:])
+        perm = torch.randperm(B, device="cuda", generator=torch.Generator("cuda").manual_seed(0))
+        permuted = net(nodes[perm], edges[perm])
+    assert torch.isfinite(full).all()
+    assert torch.equal(full[B // 2:], half)
+    assert (permuted - full[perm]).abs().max().item() <= 1e-5   # type-grouped rows move between GEMM tiles
+    assert torch.equal(permuted.argmax(1), full[perm].argmax(1))
+    net.zero_grad()
+    (Fn.kl_loss(net(nodes, edges), target)).backward()
+    g_full = [p.grad.clone() for p in net.parameters()]
+    net.zero_grad()
+    for sl in (slice(0, B // 2), slice(B // 2, B)):
+        (Fn.kl_loss(net(nodes[sl], edges[sl]), target[sl]) * 0.5).backward()
+    for a, p in zip(g_full, net.parameters()):
+        assert (a - p.grad).abs().max().item() <= 2e-5 * max(1e-3, a.abs().max().item())
+    k = 48
+    out_ref = O.forward(sd, C, nodes[:k].cpu(), edges[:k].cpu())
+    assert (full[:k].cpu() - out_ref).abs().max().item() <= LOGIT_TOL
+    assert torch.equal(full[:k].cpu().argmax(1), out_ref.argmax(1))
