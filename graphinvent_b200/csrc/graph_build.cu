@@ -244,10 +244,10 @@ int graph_fill(const float* edges, int B, int N, int Ef, int by_type, const int*
   const int* ent_off = off + (size_t)G * B;
   const int cells = N * N * G;
   const size_t smem = (size_t)3 * (cells + 2) * sizeof(unsigned short) + cells + 16;
-  static bool attr_set = false;
-  if (!attr_set) {
-    GIB_CUDA_TRY(cudaFuncSetAttribute(k0_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
+  static size_t smem_allowed = 48 * 1024;   // default dynamic-smem limit; raised on demand (opt-in up to 227 KB)
+  if (smem > smem_allowed) {
+    GIB_CUDA_TRY(cudaFuncSetAttribute(k0_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_allowed = smem;
   }
   k0_fill_kernel<<<B, 256, smem, st>>>(edges, B, N, Ef, G, cnt, off, ent_off, hdr, ga);
   GIB_LAUNCH_CHECK();
