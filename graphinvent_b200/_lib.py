@@ -31,6 +31,9 @@ HDR_E, HDR_P, HDR_TYPE_COUNT, HDR_TYPE_BASE, HDR_FLAGS = 0, 1, 2, 6, 11
 _PROTOS = {
     "gib_last_error": (ctypes.c_char_p, []),
     "gib_version": (c_i, []),
+    "gib_set_tensor_cores": (None, [c_i]),
+    "gib_get_tensor_cores": (c_i, []),
+    "gib_tc_debug": (None, [c_i]),
     "gib_graph_count_ws_bytes": (c_sz, [c_p]),
     "gib_graph_count": (c_i, [c_p, c_p, c_p, c_p]),
     "gib_graph_bytes": (c_sz, [c_p, c_p]),
@@ -46,6 +49,7 @@ _PROTOS = {
     "gib_model_backward": (c_i, [c_p] * 12),
     "gib_kl_loss_fwd_bwd": (c_i, [c_p, c_p, c_i, c_i, c_f, c_p, c_p, c_p]),
     "gib_linear_fwd": (c_i, [c_p, c_i, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
+    "gib_linear_fwd_tc": (c_i, [c_p, c_i, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
     "gib_dw_scratch_bytes": (c_sz, [c_i, c_i, c_i]),
     "gib_linear_bwd_dw": (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_p, c_p, c_i, c_i, c_p, c_p]),
     "gib_scatter_sum": (c_i, [c_p, c_p, c_i, c_p, c_p, c_p, c_ll, c_p]),

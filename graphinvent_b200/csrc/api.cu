@@ -110,7 +110,10 @@ using namespace gib;
 extern "C" {
 
 const char* gib_last_error(void) { return g_err; }
-int gib_version(void) { return 100; }
+int gib_version(void) { return 101; }
+void gib_set_tensor_cores(int on) { g_use_tc = on != 0; }
+int gib_get_tensor_cores(void) { return g_use_tc ? 1 : 0; }
+void gib_tc_debug(int mode) { g_tc_debug = mode; }
 
 static int groups_of(const gib_dims* d) { return d->model == GIB_EMN ? 1 : d->Ef; }
 
@@ -226,6 +229,13 @@ int gib_linear_fwd(const float* X, int ldx, const float* W, int ldw, const float
   p.A = X; p.lda = ldx; p.B = W; p.ldb = ldw; p.C = Y; p.ldc = ldy; p.M = M; p.N = N; p.K = K; p.bias = bias;
   p.act = act; p.mode = EPI_ACT; p.n_store = N; p.n_valid = N;
   return gemm_nt(p, ST(stream));
+}
+int gib_linear_fwd_tc(const float* X, int ldx, const float* W, int ldw, const float* bias, float* Y, int ldy, int M,
+                      int N, int K, int act, gib_stream stream) {
+  GemmNT p;
+  p.A = X; p.lda = ldx; p.B = W; p.ldb = ldw; p.C = Y; p.ldc = ldy; p.M = M; p.N = N; p.K = K; p.bias = bias;
+  p.act = act; p.mode = EPI_ACT; p.n_store = N; p.n_valid = N;
+  return gemm_nt_tc(p, ST(stream));
 }
 size_t gib_dw_scratch_bytes(int M, int Nn, int Kk) { return gemm_dw_scratch_floats(M, Nn, Kk) * sizeof(float); }
 int gib_linear_bwd_dw(const float* G, int ldg, int Nn, const float* X, int ldx, int Kk, int M, float* dW, float* dbias,

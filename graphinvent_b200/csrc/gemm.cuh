@@ -49,7 +49,12 @@ struct GemmDW {
   double work = 0;                                    // algorithmic FLOPs (0: derive)
 };
 
-int gemm_nt(const GemmNT& p, cudaStream_t st);
+int gemm_nt(const GemmNT& p, cudaStream_t st);      // dispatches to the tcgen05 path when enabled and eligible
+int gemm_nt_simt(const GemmNT& p, cudaStream_t st);
+int gemm_nt_tc(const GemmNT& p, cudaStream_t st);
+bool tc_eligible(const GemmNT& p);
+extern bool g_use_tc;
+extern int g_tc_debug;
 int gemm_dw(const GemmDW& q, cudaStream_t st);
 void gemm_dw_plan(int M, int Nn, int Kk, int* splits, int* chunk);
 size_t gemm_dw_scratch_floats(int M, int Nn, int Kk);

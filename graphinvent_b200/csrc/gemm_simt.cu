@@ -19,7 +19,7 @@ constexpr int BK = 16;
 // C[M,N] = epilogue( A[M,K] * B[N,K]^T )       (both operands K-contiguous)
 // ------------------------------------------------------------------------------------
 template <int BM, int BN, int RM, int RN>
-__global__ void __launch_bounds__(256) sgemm_nt_kernel(const GemmNT p) {
+__global__ void __launch_bounds__(256, 2) sgemm_nt_kernel(const GemmNT p) {
   static_assert((BM / (4 * RM)) * (BN / (4 * RN)) == 256, "256 threads");
   __shared__ __align__(16) float As[2][BK][BM + 4];
   __shared__ __align__(16) float Bs[2][BK][BN + 4];
@@ -163,6 +163,12 @@ __global__ void __launch_bounds__(256) sgemm_nt_kernel(const GemmNT p) {
 }
 
 int gemm_nt(const GemmNT& p, cudaStream_t st) {
+  // tensor-core path for the large GEMMs; small / skinny ones stay on the SIMT kernel
+  if (g_use_tc && p.M >= 1024 && p.N >= 48 && p.K >= 32 && tc_eligible(p)) return gemm_nt_tc(p, st);
+  return gemm_nt_simt(p, st);
+}
+
+int gemm_nt_simt(const GemmNT& p, cudaStream_t st) {
   if (p.M <= 0 || p.N <= 0) return 0;
   if (p.K % BK != 0 || (p.lda & 3) || (p.ldb & 3) || p.K <= 0) {
     set_error("gemm_nt: K=%d lda=%d ldb=%d violate the padded-layout contract", p.K, p.lda, p.ldb);
@@ -189,7 +195,7 @@ int gemm_nt(const GemmNT& p, cudaStream_t st) {
 // bias partials: Pb[z][n]  = sum_{m in chunk z} G[m,n]
 // ------------------------------------------------------------------------------------
 template <int BM, int BN, int RM, int RN>
-__global__ void __launch_bounds__(256) sgemm_tn_splitk_kernel(const GemmTN p) {
+__global__ void __launch_bounds__(256, 2) sgemm_tn_splitk_kernel(const GemmTN p) {
   __shared__ __align__(16) float As[2][BK][BM + 4];
   __shared__ __align__(16) float Bs[2][BK][BN + 4];
   const int tid = threadIdx.x;

@@ -1,0 +1,451 @@
+// tcgen05 (5th-gen tensor core) GEMM with fp32-accurate 3xTF32 operand splitting, sm_100a.
+//
+//   C[M, :N] = epi( A[M,K] * B[N,K]^T ),   A, B fp32 row-major, K-contiguous (same contract as gemm_nt)
+//
+// Why 3xTF32: the parity bar is 1e-4 on the logits; one TF32 pass is 1.8e-2 off.  Each
+// operand x is split into hi = tf32(x) and lo = tf32(x - hi); the product is accumulated as
+// hi*hi + hi*lo + lo*hi in the fp32 TMEM accumulator (the dropped lo*lo term is ~2^-22 relative).
+//
+// Structure (one persistent CTA per SM, warp-specialised, 3-stage smem ring, 2 TMEM accumulator stages):
+//   warp 0      TMA producer   : cp.async.bulk.tensor (128B swizzle) raw fp32 A/B k-blocks -> smem
+//   warps 2-5   splitters      : in-place raw -> hi, plus lo into a sibling tile (same swizzled address,
+//                                 so the swizzle pattern never has to be decoded), fence.proxy.async
+//   warp 1      MMA issuer     : 12 tcgen05.mma.kind::tf32 per k-block (4 k-steps x 3 products), accumulators
+//                                 in TMEM; tcgen05.commit frees the smem stage / publishes the accumulator
+//   warps 6-13  epilogue       : tcgen05.ld TMEM -> registers -> smem transpose -> bias / SELU / dSELU / add ->
+//                                 coalesced global stores (two warps per TMEM lane quarter)
+// Every mbarrier wait is bounded: a dead-lock turns into a trap (error at the next API call), never a hang.
+#include <cuda.h>
+
+#include "gemm.cuh"
+
+namespace gib {
+
+namespace tc {
+
+constexpr int BM = 128, BN = 128, BKF = 32;       // tile: 128 x 128 outputs, 32 floats (128 B) of K per stage
+constexpr int STAGES = 3;
+constexpr int TILE_BYTES = BM * BKF * 4;          // 16 KB per operand tile
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;       // A_hi | A_lo | B_hi | B_lo
+constexpr int EPI_WARPS = 8;                       // two warps per TMEM lane quarter, each owning 64 of the 128 columns
+constexpr int EPI_LD = 20;                         // padded row (floats) of the per-warp 32x16 epilogue staging tile
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_WARPS * 32 * EPI_LD * 4;
+constexpr int NUM_THREADS = 192 + 32 * 8;          // TMA + MMA + 4 splitter + 8 epilogue warps
+constexpr int TMEM_COLS = 512;                    // 2 stages x (main hi*hi + cross-term accumulator) x 128 fp32 columns
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: ~1 s of wall clock, then trap (surfaces as a CUDA error instead of hanging the box)
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity))
+    if (clock64() - t0 > 2000000000LL) __trap();
+}
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      :
+      : "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile (rows x 32 fp32): 8-row groups are 1024 B apart (SBO), descriptor
+// version 1 (sm_100), layout type 2 = SWIZZLE_128B.  (cute/arch/mma_sm100_desc.hpp: SmemDescriptor)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);   // start address [0,14)
+  d |= (uint64_t)1 << 16;                        // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset [32,46)
+  d |= (uint64_t)1 << 46;                        // descriptor version [46,48)
+  d |= (uint64_t)2 << 61;                        // SWIZZLE_128B [61,64)
+  return d;
+}
+// instruction descriptor, kind::tf32: D = F32 (bits 4-5 = 1), A/B = TF32 (bits 7-9, 10-12 = 2), both K-major,
+// N >> 3 at bits 17-22, M >> 4 at bits 24-28.  (InstrDescriptor in the same header)
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+
+// epilogue activation: SELU through the hardware exp2 path (MUFU), |abs err| <~ 2e-7 -- the four epilogue warps
+// must stay under the MMA time per tile, and expm1f's ~30-instruction software path does not
+__device__ __forceinline__ float act_fast(float x, int act) {
+  if (act == ACT_SELU) return x > 0.f ? GIB_SELU_SCALE * x : (GIB_SELU_SCALE * GIB_SELU_ALPHA) * (__expf(x) - 1.f);
+  if (act == ACT_TANH) return tanhf(x);
+  return x;
+}
+
+struct Params {
+  GemmNT g;
+  int m_tiles, n_tiles, k_blocks;
+  int debug;   // bit0: skip the hi/lo split (timing experiments only), bit1: skip the epilogue stores
+};
+
+template <int SPLIT>   // 0: hi = truncation, lo = exact remainder;  1: hi, lo both round-to-nearest (cvt.rna)
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                  const Params P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full_raw = bars;                 // [STAGES] TMA -> splitters
+  uint64_t* full_split = bars + STAGES;      // [STAGES] splitters -> MMA
+  uint64_t* empty = bars + 2 * STAGES;       // [STAGES] MMA -> TMA
+  uint64_t* acc_full = bars + 3 * STAGES;    // [2] MMA -> epilogue
+  uint64_t* acc_empty = bars + 3 * STAGES + 2;  // [2] epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const GemmNT& g = P.g;
+  const int num_tiles = P.m_tiles * P.n_tiles;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_raw[s], 1);
+      mbar_init(&full_split[s], 128);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&acc_full[a], 1);
+      mbar_init(&acc_empty[a], 32 * EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM allocation is a whole-warp operation; the same warp frees it
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / P.n_tiles) * BM, n0 = (tile % P.n_tiles) * BN;
+        for (int kb = 0; kb < P.k_blocks; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* st = smem + stage * STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_raw[stage], 2 * TILE_BYTES);
+          tma_load_2d(&map_a, &full_raw[stage], st, kb * BKF, m0);
+          tma_load_2d(&map_b, &full_raw[stage], st + 2 * TILE_BYTES, kb * BKF, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        // Two accumulators per tile.  The tensor core adds into TMEM with truncation, one rounding per MMA; the
+        // hi*lo / lo*hi products are 2^-11 of the hi*hi ones, so giving them their own accumulator keeps their
+        // 2/3 of the roundings away from the large running sum (measured: error / 3, back to fp32-FMA level).
+        const uint32_t tmem_d = tmem_base + acc * 2 * BN;        // sum of hi*hi
+        const uint32_t tmem_x = tmem_d + BN;                     // sum of hi*lo + lo*hi
+        for (int kb = 0; kb < P.k_blocks; ++kb) {
+          mbar_wait(&full_split[stage], phase);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(smem + stage * STAGE_BYTES);
+          const uint64_t d_ahi = make_desc(a_hi), d_alo = make_desc(a_hi + TILE_BYTES);
+          const uint64_t d_bhi = make_desc(a_hi + 2 * TILE_BYTES), d_blo = make_desc(a_hi + 3 * TILE_BYTES);
+          // grouped by accumulator so that consecutive MMAs chain on the same TMEM tile
+#pragma unroll
+          for (int k = 0; k < BKF / 8; ++k) {
+            const uint64_t adv = (uint64_t)(k * 32 >> 4);     // 8 tf32 = 32 B further along K, in 16 B units
+            umma_tf32(tmem_d, d_ahi + adv, d_bhi + adv, IDESC, (kb | k) != 0);
+          }
+#pragma unroll
+          for (int k = 0; k < BKF / 8; ++k) {
+            const uint64_t adv = (uint64_t)(k * 32 >> 4);
+            umma_tf32(tmem_x, d_alo + adv, d_bhi + adv, IDESC, (kb | k) != 0);
+            umma_tf32(tmem_x, d_ahi + adv, d_blo + adv, IDESC, 1);
+          }
+          umma_commit(&empty[stage]);                           // frees the smem stage when the MMAs retire
+          if (kb == P.k_blocks - 1) umma_commit(&acc_full[acc]);  // accumulator complete
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp < 6) {
+    // ================= splitters: raw fp32 -> (hi, lo) TF32 pairs, in place =================
+    const int t = threadIdx.x - 64;  // 0..127
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < P.k_blocks; ++kb) {
+        mbar_wait(&full_raw[stage], phase);
+        uint8_t* st = smem + stage * STAGE_BYTES;
+        if (!(P.debug & 1))
+#pragma unroll
+        for (int op = 0; op < 2; ++op) {
+          float4* hi = reinterpret_cast<float4*>(st + op * 2 * TILE_BYTES);
+          float4* lo = reinterpret_cast<float4*>(st + op * 2 * TILE_BYTES + TILE_BYTES);
+#pragma unroll
+          for (int i = 0; i < TILE_BYTES / 16 / 128; ++i) {
+            const int c = t + i * 128;
+            const float4 v = hi[c];
+            float4 h, l;
+            if (SPLIT == 1) {    // round-to-nearest split: 3 conversions per element, smallest error
+              h.x = __uint_as_float(to_tf32(v.x)); l.x = __uint_as_float(to_tf32(v.x - h.x));
+              h.y = __uint_as_float(to_tf32(v.y)); l.y = __uint_as_float(to_tf32(v.y - h.y));
+              h.z = __uint_as_float(to_tf32(v.z)); l.z = __uint_as_float(to_tf32(v.z - h.z));
+              h.w = __uint_as_float(to_tf32(v.w)); l.w = __uint_as_float(to_tf32(v.w - h.w));
+            } else {             // hi = top 19 bits (exact tf32), lo = x - hi (exact in fp32; the MMA reads its top 19 bits)
+              h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
+              h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
+              h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
+              h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
+            }
+            hi[c] = h;
+            lo[c] = l;
+          }
+        }
+        fence_proxy_async();           // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+        mbar_arrive(&full_split[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ================= epilogue: TMEM -> registers -> smem transpose -> coalesced global =================
+    // tcgen05.ld hands each lane one accumulator ROW; storing that directly would scatter 16-byte pieces over 32
+    // rows per instruction (measured: 0.6 TB/s).  Each warp therefore bounces 32x32 chunks through a private
+    // padded smem tile and writes 4 rows x 128 contiguous bytes per instruction; bias / activation / aux math runs
+    // in that coalesced domain, so the aux operand (dSELU source or residual) is read coalesced as well.
+    const int q = warp & 3;                    // TMEM lane quarter this warp may access
+    const int half = (warp - 6) >> 2;          // which 64-column half of the tile this warp drains
+    float* stg = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256) + (warp - 6) * (32 * EPI_LD);
+    const int rr = lane >> 2, cc = (lane & 3) * 4;
+    const bool vec_c = (g.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
+    const bool vec_x = g.aux && (g.ldaux & 3) == 0 && ((reinterpret_cast<uintptr_t>(g.aux) & 15) == 0);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int m0 = (tile / P.n_tiles) * BM, n0 = (tile % P.n_tiles) * BN;
+      mbar_wait(&acc_full[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int chunk = 0; chunk < 4; ++chunk) {
+        const int col0 = half * 64 + chunk * 16;
+        uint32_t r[16], rx[16];
+        __syncwarp();
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + acc * 2 * BN + col0, r);
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + acc * 2 * BN + BN + col0, rx);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4)
+          *reinterpret_cast<float4*>(stg + lane * EPI_LD + j4 * 4) =
+              make_float4(__uint_as_float(r[j4 * 4 + 0]) + __uint_as_float(rx[j4 * 4 + 0]),
+                          __uint_as_float(r[j4 * 4 + 1]) + __uint_as_float(rx[j4 * 4 + 1]),
+                          __uint_as_float(r[j4 * 4 + 2]) + __uint_as_float(rx[j4 * 4 + 2]),
+                          __uint_as_float(r[j4 * 4 + 3]) + __uint_as_float(rx[j4 * 4 + 3]));
+        __syncwarp();
+        const int n = n0 + col0 + cc;
+        if (n < g.n_store && !(P.debug & 2)) {
+          float bj[4] = {0.f, 0.f, 0.f, 0.f};
+          if (g.mode == EPI_ACT && g.bias) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (n + j < g.N) bj[j] = __ldg(g.bias + n + j);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int row = i * 8 + rr;
+            const int m = m0 + q * 32 + row;
+            if (m >= g.M) continue;
+            const float4 a4 = *reinterpret_cast<const float4*>(stg + row * EPI_LD + cc);
+            float v[4] = {a4.x, a4.y, a4.z, a4.w};
+            float x[4] = {0.f, 0.f, 0.f, 0.f};
+            if (g.mode != EPI_ACT) {
+              const float* ax = g.aux + (size_t)m * g.ldaux + n;
+              if (vec_x && n + 3 < g.n_store) {
+                const float4 t4 = *reinterpret_cast<const float4*>(ax);
+                x[0] = t4.x; x[1] = t4.y; x[2] = t4.z; x[3] = t4.w;
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  if (n + j < g.n_store) x[j] = ax[j];
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (g.mode == EPI_ACT) v[j] = act_fast(v[j] + bj[j], g.act);
+              else if (g.mode == EPI_MUL_DACT) v[j] = v[j] * dact_from_out(x[j], g.act);
+              else v[j] = v[j] + x[j];
+              if (n + j >= g.n_valid) v[j] = 0.f;
+            }
+            float* dst = g.C + (size_t)m * g.ldc + n;
+            if (vec_c && n + 3 < g.n_store) {
+              *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (n + j < g.n_store) dst[j] = v[j];
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static int make_map(CUtensorMap* map, const float* base, int rows, int cols, int ld) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return -4; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)BKF, (cuuint32_t)BM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d ld=%d", (int)r, rows, cols, ld); return -4; }
+  return 0;
+}
+
+}  // namespace tc
+
+bool g_use_tc = true;
+int g_tc_debug = 0;
+
+bool tc_eligible(const GemmNT& p) {
+  return p.M >= 1 && p.N >= 1 && p.K >= 16 && (p.K % 16) == 0 && (p.lda % 4) == 0 && (p.ldb % 4) == 0 &&
+         (reinterpret_cast<uintptr_t>(p.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.B) & 15) == 0;
+}
+
+int gemm_nt_tc(const GemmNT& p, cudaStream_t st) {
+  using namespace tc;
+  if (p.M <= 0 || p.N <= 0) return 0;
+  if (!tc_eligible(p)) { set_error("gemm_nt_tc: operands violate the TMA alignment contract"); return -2; }
+  static int num_sms = 0;
+  static bool attr_done = false;
+  if (!attr_done) {
+    int dev = 0;
+    GIB_CUDA_TRY(cudaGetDevice(&dev));
+    GIB_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    GIB_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_nt_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    GIB_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_nt_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_done = true;
+  }
+  CUtensorMap ma, mb;
+  GIB_TRY(make_map(&ma, p.A, p.M, p.K, p.lda));
+  GIB_TRY(make_map(&mb, p.B, p.N, p.K, p.ldb));
+  Params P;
+  P.g = p;
+  P.m_tiles = ceil_div(p.M, BM);
+  P.n_tiles = ceil_div(p.N, BN);
+  P.k_blocks = ceil_div(p.K, BKF);
+  P.debug = g_tc_debug;
+  const int tiles = P.m_tiles * P.n_tiles;
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  ProfScope prof(PROF_GEMM_NT, p.work > 0 ? p.work : 2.0 * p.M * (double)p.N * p.K, st);
+  // default: round-to-nearest split (same speed -- the splitters are smem-bound -- and ~30% smaller error)
+  if (g_tc_debug & 4) tc_gemm_nt_kernel<0><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, P);
+  else tc_gemm_nt_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, P);
+  GIB_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace gib

@@ -153,7 +153,7 @@ __global__ void gather_rows_kernel(float4* __restrict__ dst, const float4* __res
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
   if (s >= 0) {
     v = __ldg(h + (size_t)s * ld4 + c);
-    if (scale) {
+    if (scale && w) {
       const float ww = __ldg(w + p);
       v.x *= ww; v.y *= ww; v.z *= ww; v.w *= ww;
     }
@@ -186,12 +186,26 @@ __global__ void __launch_bounds__(256) scatter_sum_kernel(float4* __restrict__ o
   const int c = (int)(idx % ld4);
   const int q0 = __ldg(ptr + s), q1 = __ldg(ptr + s + 1);
   float4 acc = accumulate ? out[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int q = q0; q < q1; ++q) {
-    const int p = __ldg(ent + q);
-    const float ww = w ? __ldg(w + p) : 1.f;
-    const float4 v = __ldg(msg + (size_t)p * ld4 + c);
-    acc.x = fmaf(ww, v.x, acc.x); acc.y = fmaf(ww, v.y, acc.y);
-    acc.z = fmaf(ww, v.z, acc.z); acc.w = fmaf(ww, v.w, acc.w);
+  // 4 entries per trip: the index loads, then the row loads, are issued back to back so that up to four
+  // 16-byte row reads per thread are in flight (molecular graphs: degree <= 4 almost always -> one trip).
+  // The accumulation order stays ascending in q (fixed order => bit-stable results).
+  for (int q = q0; q < q1; q += 4) {
+    int p[4];
+    float ww[4];
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) p[u] = (q + u < q1) ? __ldg(ent + q + u) : -1;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      ww[u] = (p[u] >= 0 && w) ? __ldg(w + p[u]) : 1.f;
+      v[u] = (p[u] >= 0) ? __ldg(msg + (size_t)p[u] * ld4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (p[u] >= 0) {
+        acc.x = fmaf(ww[u], v[u].x, acc.x); acc.y = fmaf(ww[u], v[u].y, acc.y);
+        acc.z = fmaf(ww[u], v[u].z, acc.z); acc.w = fmaf(ww[u], v[u].w, acc.w);
+      }
   }
   out[idx] = acc;
 }
@@ -254,12 +268,12 @@ __global__ void __launch_bounds__(256) seg_softmax_fwd_kernel(float* __restrict_
     float mx = -INFINITY;
     for (int q = q0; q < q1; ++q) {
       const int p = __ldg(ent + q);
-      mx = fmaxf(mx, __ldg(w + p) * __ldg(EN + (size_t)p * ld + c));
+      mx = fmaxf(mx, (w ? __ldg(w + p) : 1.f) * __ldg(EN + (size_t)p * ld + c));
     }
     float den = 0.f, num = 0.f;
     for (int q = q0; q < q1; ++q) {
       const int p = __ldg(ent + q);
-      const float ww = __ldg(w + p);
+      const float ww = w ? __ldg(w + p) : 1.f;
       const float e = expf(ww * __ldg(EN + (size_t)p * ld + c) - mx);
       den += e;
       num = fmaf(e, ww * __ldg(EM + (size_t)p * ld + c), num);
@@ -294,12 +308,12 @@ __global__ void __launch_bounds__(256) seg_softmax_bwd_kernel(float* __restrict_
   float mx = -INFINITY;
   for (int q = q0; q < q1; ++q) {
     const int p = __ldg(ent + q);
-    mx = fmaxf(mx, __ldg(w + p) * __ldg(EN + (size_t)p * ld + c));
+    mx = fmaxf(mx, (w ? __ldg(w + p) : 1.f) * __ldg(EN + (size_t)p * ld + c));
   }
   float den = 0.f, dot = 0.f;
   for (int q = q0; q < q1; ++q) {
     const int p = __ldg(ent + q);
-    const float ww = __ldg(w + p);
+    const float ww = w ? __ldg(w + p) : 1.f;
     const float e = expf(ww * __ldg(EN + (size_t)p * ld + c) - mx);
     den += e;
     dot = fmaf(e, ww * __ldg(EM + (size_t)p * ld + c) * d, dot);
@@ -308,7 +322,7 @@ __global__ void __launch_bounds__(256) seg_softmax_bwd_kernel(float* __restrict_
   dot *= inv;
   for (int q = q0; q < q1; ++q) {
     const int p = __ldg(ent + q);
-    const float ww = __ldg(w + p);
+    const float ww = w ? __ldg(w + p) : 1.f;
     const float en = __ldg(EN + (size_t)p * ld + c), em = __ldg(EM + (size_t)p * ld + c);
     const float a = expf(ww * en - mx) * inv;
     GM[(size_t)p * ld + c] = ww * a * d * dselu_from_out(em);

@@ -185,6 +185,7 @@ int make_run(const gib_dims& d, const int* hdr, Run& r) {
   for (int g = 0; g < 4; ++g) r.tc[g] = g < G ? hdr[HDR_TYPE_COUNT + g] : 0;
   for (int g = 0; g < 5; ++g) r.tb[g] = g <= G ? hdr[HDR_TYPE_BASE + g] : r.P;
   r.ngroups = G;
+  r.unit_bonds = (hdr[HDR_FLAGS] & GRAPH_FLAG_NONBINARY) == 0;   // every bond value is exactly 1: skip the w reads
   r.S = (long long)d.B * d.N;
   if (d.B < 1 || r.E < 0 || r.P < r.E) {
     set_error("make_run: inconsistent graph header (B=%d E=%d P=%d)", d.B, r.E, r.P);
@@ -437,7 +438,7 @@ static int node_model_forward(const Run& r, float* out) {
   for (int t = 0; t < d.T; ++t) {
     const float* h = r.ws + L.h[t];
     // mpnn.py:286-288 scales the neighbour state by the bond value for GGNN only
-    GIB_TRY(gather_rows(r.ws + L.x0[t], h, Hp, r.ga.ent_src, r.ga.ent_w, d.model == GIB_GGNN, r.P, r.st));
+    GIB_TRY(gather_rows(r.ws + L.x0[t], h, Hp, r.ga.ent_src, r.w(), d.model == GIB_GGNN, r.P, r.st));
     for (int g = 0; g < r.ngroups; ++g) {
       GIB_TRY(mlp_forward(r, pl.msg[g], r.ws + L.x0[t], L.msg[t], r.tb[g], r.tc[g]));
       if (d.model == GIB_ATTGGNN) GIB_TRY(mlp_forward(r, pl.att[g], r.ws + L.x0[t], L.att[t], r.tb[g], r.tc[g]));
@@ -445,9 +446,9 @@ static int node_model_forward(const Run& r, float* out) {
     const float* msgs = r.ws + L.msg[t].y[pl.msg[0].n];
     if (d.model == GIB_ATTGGNN)
       GIB_TRY(seg_softmax_fwd(r.ws + L.msum[t], msgs, r.ws + L.att[t].y[pl.att[0].n], Mp, r.ga.dst_ptr, r.ga.dst_ent,
-                              r.ga.ent_w, S, r.st));
+                              r.w(), S, r.st));
     else
-      GIB_TRY(scatter_sum(r.ws + L.msum[t], msgs, Mp, r.ga.dst_ptr, r.ga.dst_ent, r.ga.ent_w, 0, S, r.st));
+      GIB_TRY(scatter_sum(r.ws + L.msum[t], msgs, Mp, r.ga.dst_ptr, r.ga.dst_ent, r.w(), 0, S, r.st));
     GemmNT p;
     p.A = r.ws + L.msum[t]; p.lda = Mp; p.B = r.packed + ih.ow; p.ldb = ih.Cp; p.C = r.ws + L.gi[t]; p.ldc = ih.Rp;
     p.M = (int)S; p.N = ih.Rp; p.K = ih.Cp; p.bias = r.packed + ih.ob; p.act = ACT_NONE; p.mode = EPI_ACT;
@@ -503,9 +504,9 @@ static int node_model_backward(const Run& r, const BwdBufs& bb, const float* out
       GIB_CUDA_TRY(cudaMemsetAsync(T1, 0, (size_t)r.P * Mp * sizeof(float), r.st));
       GIB_CUDA_TRY(cudaMemsetAsync(T2, 0, (size_t)r.P * Mp * sizeof(float), r.st));
       GIB_TRY(seg_softmax_bwd(T1, T2, sc + bb.dmsum, r.ws + L.msg[t].y[nm], r.ws + L.att[t].y[pl.att[0].n], Mp,
-                              r.ga.dst_ptr, r.ga.dst_ent, r.ga.ent_w, S, r.st));
+                              r.ga.dst_ptr, r.ga.dst_ent, r.w(), S, r.st));
     } else {
-      GIB_TRY(scatter_bwd(T1, sc + bb.dmsum, r.ws + L.msg[t].y[nm], Mp, r.ga.ent_dst, r.ga.ent_w, pl.msg[0].act, r.P,
+      GIB_TRY(scatter_bwd(T1, sc + bb.dmsum, r.ws + L.msg[t].y[nm], Mp, r.ga.ent_dst, r.w(), pl.msg[0].act, r.P,
                           r.st));
     }
     for (int g = 0; g < r.ngroups; ++g) {
@@ -517,7 +518,7 @@ static int node_model_backward(const Run& r, const BwdBufs& bb, const float* out
                              dx0 + ro * Hp, Hp, dx0 + ro * Hp));
     }
     // dh[t][src] += (w) dX0   -- deterministic gather-reduce over the by-source CSR
-    GIB_TRY(scatter_sum(dh, dx0, Hp, r.ga.src_ptr, r.ga.src_ent, d.model == GIB_GGNN ? r.ga.ent_w : nullptr, 1, S,
+    GIB_TRY(scatter_sum(dh, dx0, Hp, r.ga.src_ptr, r.ga.src_ent, d.model == GIB_GGNN ? r.w() : nullptr, 1, S,
                         r.st));
   }
   return 0;

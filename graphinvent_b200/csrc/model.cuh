@@ -69,6 +69,8 @@ struct Run {
   Plan pl;
   Layout L;
   int E = 0, P = 0, ngroups = 0;
+  bool unit_bonds = false;
+  const float* w() const { return unit_bonds ? nullptr : ga.ent_w; }
   int tc[4], tb[5];
   long long S = 0;
   const float* nodes = nullptr;

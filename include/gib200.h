@@ -67,6 +67,11 @@ enum {
 
 const char* gib_last_error(void);
 int gib_version(void);
+/* tcgen05 3xTF32 GEMM path on (default) / off (fp32 SIMT GEMMs only); process-wide switch */
+void gib_set_tensor_cores(int on);
+int gib_get_tensor_cores(void);
+/* timing experiments only (results become wrong): bit0 skip the hi/lo split, bit1 skip epilogue stores */
+void gib_tc_debug(int mode);
 
 /* ---- K0: edges -> bond entries + CSR.  Replaces summation_mpnn.py:102-118,
  *      aggregation_mpnn.py:105-148, edge_mpnn.py:104-173. ------------------------------- */
@@ -112,6 +117,9 @@ int gib_kl_loss_fwd_bwd(const float* out, const float* target, int B, int apd, f
 /* Y = act(X W^T + b); X [M, ldx], W packed [Np, Kp] (ldw), Y [M, ldy]; act 0 none / 1 selu / 2 tanh */
 int gib_linear_fwd(const float* X, int ldx, const float* W, int ldw, const float* bias, float* Y, int ldy,
                    int M, int N, int K, int act, gib_stream stream);
+/* same contract, forced onto the tcgen05 3xTF32 kernel regardless of the size heuristics */
+int gib_linear_fwd_tc(const float* X, int ldx, const float* W, int ldw, const float* bias, float* Y, int ldy,
+                      int M, int N, int K, int act, gib_stream stream);
 /* dW[R,C] += G^T X, dbias[R] += colsum(G); G [M, ldg], X [M, ldx]; scratch from gib_dw_scratch_bytes */
 size_t gib_dw_scratch_bytes(int M, int Nn, int Kk);
 int gib_linear_bwd_dw(const float* G, int ldg, int Nn, const float* X, int ldx, int Kk, int M, float* dW,
