@@ -57,6 +57,9 @@ extern bool g_use_tc;
 extern int g_tc_debug;
 int gemm_dw(const GemmDW& q, cudaStream_t st);
 void gemm_dw_plan(int M, int Nn, int Kk, int* splits, int* chunk);
+void tc_dw_plan(int M, int Nn, int Kk, int* splits, int* chunk);
+bool tc_dw_eligible(const GemmDW& q);
+int gemm_dw_tc_partials(const GemmDW& q, int* splits_out, cudaStream_t st);
 size_t gemm_dw_scratch_floats(int M, int Nn, int Kk);
 
 }  // namespace gib

@@ -10,10 +10,12 @@
 // extent K is a multiple of 16.  Replaces the ATen `addmm`/`mm` call sites of
 // reference gnn/modules.py:162-170 (MLP), gnn/mpnn.py:296 (GRUCell) and their autograd.
 #include "gemm.cuh"
+#include "ops.cuh"
 
 namespace gib {
 
 constexpr int BK = 16;
+constexpr int kColsumSplits = 64;   // row chunks of the two-stage bias-gradient column sum
 
 // ------------------------------------------------------------------------------------
 // C[M,N] = epilogue( A[M,K] * B[N,K]^T )       (both operands K-contiguous)
@@ -335,10 +337,32 @@ __global__ void reduce_db_kernel(const float* __restrict__ wsb, int splits, int 
   out[r] += s;
 }
 
+// part[z][n] = sum over the z-th row chunk of G[m, n]  (fixed order inside the chunk; chunks reduced in order)
+__global__ void __launch_bounds__(256) colsum_partial_kernel(float* __restrict__ part, const float* __restrict__ G,
+                                                             int ldg, int M, int Nn) {
+  __shared__ float sm[8][33];
+  const int n = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int wy = threadIdx.x >> 5;
+  const int rows = ceil_div(M, (int)gridDim.y);
+  const int m0 = blockIdx.y * rows, m1 = min(M, m0 + rows);
+  float s = 0.f;
+  if (n < Nn)
+    for (int m = m0 + wy; m < m1; m += 8) s += G[(size_t)m * ldg + n];
+  sm[wy][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (wy == 0 && n < Nn) {
+    float t = 0.f;
+    for (int k = 0; k < 8; ++k) t += sm[k][threadIdx.x];
+    part[(size_t)blockIdx.y * Nn + n] = t;
+  }
+}
+
 size_t gemm_dw_scratch_floats(int M, int Nn, int Kk) {
-  int splits, chunk;
+  int splits, chunk, s2, c2;
   gemm_dw_plan(M, Nn, Kk, &splits, &chunk);
-  return (size_t)splits * Nn * Kk + (size_t)splits * Nn;
+  tc_dw_plan(M, Nn, Kk, &s2, &c2);       // the tensor-core path may pick a different split count
+  if (s2 > splits) splits = s2;
+  return (size_t)splits * Nn * Kk + (size_t)(splits > kColsumSplits ? splits : kColsumSplits) * Nn;
 }
 
 void gemm_dw_plan(int M, int Nn, int Kk, int* splits, int* chunk) {
@@ -362,6 +386,24 @@ int gemm_dw(const GemmDW& q, cudaStream_t st) {
     return -2;
   }
   ProfScope prof(PROF_GEMM_DW, q.work > 0 ? q.work : 2.0 * q.M * (double)q.R * q.C, st);
+  if (g_use_tc && q.dW && tc_dw_eligible(q)) {
+    // tensor-core partials (tcgen05, MN-major operands straight from the row-major activations), then the same
+    // fixed-order split reduction; the bias gradient is a separate column sum of G
+    int tsplits = 0;
+    GIB_TRY(gemm_dw_tc_partials(q, &tsplits, st));
+    const long long tot = (long long)q.R * q.C;
+    reduce_dw_kernel<<<(unsigned)ceil_div_ll(tot, 256), 256, 0, st>>>(q.scratch, tsplits, q.Nn, q.Kk, q.dW, q.R, q.C,
+                                                                     q.Rb, q.Rbp, q.rs, q.cs);
+    GIB_LAUNCH_CHECK();
+    if (q.dbias) {
+      float* part = q.scratch + (size_t)tsplits * q.Nn * q.Kk;     // [kColsumSplits][Nn] partial column sums
+      colsum_partial_kernel<<<dim3(ceil_div(q.Nn, 32), kColsumSplits), 256, 0, st>>>(part, q.G, q.ldg, q.M, q.Nn);
+      GIB_LAUNCH_CHECK();
+      reduce_db_kernel<<<ceil_div(q.R, 256), 256, 0, st>>>(part, kColsumSplits, q.Nn, q.dbias, q.R, q.Rb, q.Rbp);
+      GIB_LAUNCH_CHECK();
+    }
+    return 0;
+  }
   int splits, chunk;
   gemm_dw_plan(q.M, q.Nn, q.Kk, &splits, &chunk);
   GemmTN p;

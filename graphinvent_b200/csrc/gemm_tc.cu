@@ -120,9 +120,24 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                        // SWIZZLE_128B [61,64)
   return d;
 }
+// MN-major operand tile as TMA lays down four [32 rows x 32 floats] boxes back to back.  For MN-major 32-bit
+// operands the only UMMA layout is SWIZZLE_128B_BASE32B (layout type 1, Swizzle<2,5,2>: 32-byte chunks XOR-ed with
+// the row index mod 4, 4-row atoms; cutlass sm100_common.inl:92) = TMA's CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+// Along MN 32 floats are contiguous (one 128 B row), the next 32-float column group starts 4096 B later (LBO),
+// reduction rows are 128 B apart and 4-row atoms 512 B apart (SBO).  One tf32 MMA consumes 8 rows = 1024 B.
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(4096 >> 4) << 16;              // leading byte offset: next column group
+  d |= (uint64_t)(512 >> 4) << 32;               // stride byte offset: next 4-row atom
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;                        // SWIZZLE_128B_BASE32B
+  return d;
+}
 // instruction descriptor, kind::tf32: D = F32 (bits 4-5 = 1), A/B = TF32 (bits 7-9, 10-12 = 2), both K-major,
 // N >> 3 at bits 17-22, M >> 4 at bits 24-28.  (InstrDescriptor in the same header)
 constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+constexpr uint32_t IDESC_TN = IDESC | (1u << 15) | (1u << 16);   // A and B MN-major (bits 15, 16)
 
 __device__ __forceinline__ uint32_t to_tf32(float x) {
   uint32_t r;
@@ -141,6 +156,9 @@ __device__ __forceinline__ float act_fast(float x, int act) {
 struct Params {
   GemmNT g;
   int m_tiles, n_tiles, k_blocks;
+  // TN (weight-gradient) mode: P[z][n][k] = sum_{m in chunk z} G[m,n] X[m,k]; operands are the row-major
+  // activations themselves (MN-major for the MMA), g.A = G, g.B = X, g.C = split-K workspace
+  int tn, splits, chunk_rows, tn_rows, tn_nn, tn_kk;
   int debug;   // bit0: skip the hi/lo split (timing experiments only), bit1: skip the epilogue stores
 };
 
@@ -160,7 +178,8 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const GemmNT& g = P.g;
-  const int num_tiles = P.m_tiles * P.n_tiles;
+  const int tiles_mn = P.m_tiles * P.n_tiles;
+  const int num_tiles = tiles_mn * (P.tn ? P.splits : 1);   // TN: one work item per (tile, reduction chunk)
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -189,14 +208,26 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
+        const int tile = item % tiles_mn, z = item / tiles_mn;
         const int m0 = (tile / P.n_tiles) * BM, n0 = (tile % P.n_tiles) * BN;
-        for (int kb = 0; kb < P.k_blocks; ++kb) {
+        const int r0 = z * P.chunk_rows;
+        const int nkb = P.tn ? ceil_div(min(P.tn_rows, r0 + P.chunk_rows) - r0, BKF) : P.k_blocks;
+        for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* st = smem + stage * STAGE_BYTES;
           mbar_arrive_expect_tx(&full_raw[stage], 2 * TILE_BYTES);
-          tma_load_2d(&map_a, &full_raw[stage], st, kb * BKF, m0);
-          tma_load_2d(&map_b, &full_raw[stage], st + 2 * TILE_BYTES, kb * BKF, n0);
+          if (!P.tn) {
+            tma_load_2d(&map_a, &full_raw[stage], st, kb * BKF, m0);
+            tma_load_2d(&map_b, &full_raw[stage], st + 2 * TILE_BYTES, kb * BKF, n0);
+          } else {
+            const int row = r0 + kb * BKF;           // 32 reduction rows per stage
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {            // four 32-float column groups per operand
+              tma_load_2d(&map_a, &full_raw[stage], st + j * 4096, m0 + 32 * j, row);
+              tma_load_2d(&map_b, &full_raw[stage], st + 2 * TILE_BYTES + j * 4096, n0 + 32 * j, row);
+            }
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -207,7 +238,10 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int item = blockIdx.x; item < num_tiles; item += gridDim.x, ++it) {
+        const int z = item / tiles_mn;
+        const int r0 = z * P.chunk_rows;
+        const int nkb = P.tn ? ceil_div(min(P.tn_rows, r0 + P.chunk_rows) - r0, BKF) : P.k_blocks;
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);
@@ -217,26 +251,32 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         // 2/3 of the roundings away from the large running sum (measured: error / 3, back to fp32-FMA level).
         const uint32_t tmem_d = tmem_base + acc * 2 * BN;        // sum of hi*hi
         const uint32_t tmem_x = tmem_d + BN;                     // sum of hi*lo + lo*hi
-        for (int kb = 0; kb < P.k_blocks; ++kb) {
+        const uint32_t idesc = P.tn ? IDESC_TN : IDESC;
+        for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full_split[stage], phase);
           tc_fence_after();
           const uint32_t a_hi = smem_u32(smem + stage * STAGE_BYTES);
-          const uint64_t d_ahi = make_desc(a_hi), d_alo = make_desc(a_hi + TILE_BYTES);
-          const uint64_t d_bhi = make_desc(a_hi + 2 * TILE_BYTES), d_blo = make_desc(a_hi + 3 * TILE_BYTES);
+          uint64_t d_ahi, d_alo, d_bhi, d_blo, kstep;
+          if (!P.tn) {
+            d_ahi = make_desc(a_hi); d_alo = make_desc(a_hi + TILE_BYTES);
+            d_bhi = make_desc(a_hi + 2 * TILE_BYTES); d_blo = make_desc(a_hi + 3 * TILE_BYTES);
+            kstep = 32 >> 4;       // 8 tf32 = 32 B further along K, in 16 B units
+          } else {
+            d_ahi = make_desc_mn(a_hi); d_alo = make_desc_mn(a_hi + TILE_BYTES);
+            d_bhi = make_desc_mn(a_hi + 2 * TILE_BYTES); d_blo = make_desc_mn(a_hi + 3 * TILE_BYTES);
+            kstep = 1024 >> 4;     // 8 reduction rows = one 1024 B swizzle atom further
+          }
           // grouped by accumulator so that consecutive MMAs chain on the same TMEM tile
 #pragma unroll
-          for (int k = 0; k < BKF / 8; ++k) {
-            const uint64_t adv = (uint64_t)(k * 32 >> 4);     // 8 tf32 = 32 B further along K, in 16 B units
-            umma_tf32(tmem_d, d_ahi + adv, d_bhi + adv, IDESC, (kb | k) != 0);
-          }
+          for (int k = 0; k < BKF / 8; ++k)
+            umma_tf32(tmem_d, d_ahi + k * kstep, d_bhi + k * kstep, idesc, (kb | k) != 0);
 #pragma unroll
           for (int k = 0; k < BKF / 8; ++k) {
-            const uint64_t adv = (uint64_t)(k * 32 >> 4);
-            umma_tf32(tmem_x, d_alo + adv, d_bhi + adv, IDESC, (kb | k) != 0);
-            umma_tf32(tmem_x, d_ahi + adv, d_blo + adv, IDESC, 1);
+            umma_tf32(tmem_x, d_alo + k * kstep, d_bhi + k * kstep, idesc, (kb | k) != 0);
+            umma_tf32(tmem_x, d_ahi + k * kstep, d_blo + k * kstep, idesc, 1);
           }
-          umma_commit(&empty[stage]);                           // frees the smem stage when the MMAs retire
-          if (kb == P.k_blocks - 1) umma_commit(&acc_full[acc]);  // accumulator complete
+          umma_commit(&empty[stage]);                        // frees the smem stage when the MMAs retire
+          if (kb == nkb - 1) umma_commit(&acc_full[acc]);    // accumulators complete
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -246,8 +286,10 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int t = threadIdx.x - 64;  // 0..127
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      for (int kb = 0; kb < P.k_blocks; ++kb) {
+    for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
+      const int r0s = (item / tiles_mn) * P.chunk_rows;
+      const int nkb = P.tn ? ceil_div(min(P.tn_rows, r0s + P.chunk_rows) - r0s, BKF) : P.k_blocks;
+      for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(&full_raw[stage], phase);
         uint8_t* st = smem + stage * STAGE_BYTES;
         if (!(P.debug & 1))
@@ -293,7 +335,9 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const bool vec_c = (g.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
     const bool vec_x = g.aux && (g.ldaux & 3) == 0 && ((reinterpret_cast<uintptr_t>(g.aux) & 15) == 0);
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int item = blockIdx.x; item < num_tiles; item += gridDim.x, ++it) {
+      const int tile = item % tiles_mn;
+      float* const Cbase = g.C + (P.tn ? (size_t)(item / tiles_mn) * P.tn_nn * P.tn_kk : (size_t)0);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int m0 = (tile / P.n_tiles) * BM, n0 = (tile % P.n_tiles) * BN;
@@ -349,7 +393,7 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               else v[j] = v[j] + x[j];
               if (n + j >= g.n_valid) v[j] = 0.f;
             }
-            float* dst = g.C + (size_t)m * g.ldc + n;
+            float* dst = Cbase + (size_t)m * g.ldc + n;
             if (vec_c && n + 3 < g.n_store) {
               *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
             } else {
@@ -391,15 +435,16 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-static int make_map(CUtensorMap* map, const float* base, int rows, int cols, int ld) {
+static int make_map(CUtensorMap* map, const float* base, int rows, int cols, int ld, int box_rows = BM,
+                    CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return -4; }
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {(cuuint32_t)BKF, (cuuint32_t)BM};
+  cuuint32_t box[2] = {(cuuint32_t)BKF, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d ld=%d", (int)r, rows, cols, ld); return -4; }
   return 0;
@@ -437,6 +482,7 @@ int gemm_nt_tc(const GemmNT& p, cudaStream_t st) {
   P.m_tiles = ceil_div(p.M, BM);
   P.n_tiles = ceil_div(p.N, BN);
   P.k_blocks = ceil_div(p.K, BKF);
+  P.tn = 0; P.splits = 1; P.chunk_rows = 0; P.tn_rows = 0; P.tn_nn = 0; P.tn_kk = 0;
   P.debug = g_tc_debug;
   const int tiles = P.m_tiles * P.n_tiles;
   const int grid = tiles < num_sms ? tiles : num_sms;
@@ -445,6 +491,59 @@ int gemm_nt_tc(const GemmNT& p, cudaStream_t st) {
   if (g_tc_debug & 4) tc_gemm_nt_kernel<0><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, P);
   else tc_gemm_nt_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, P);
   GIB_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- weight-gradient GEMM on the tensor cores --------------------------------------------------------------
+void tc_dw_plan(int M, int Nn, int Kk, int* splits, int* chunk) {
+  const int tiles = ceil_div(Nn, tc::BM) * ceil_div(Kk, tc::BN);
+  int s = ceil_div(148, tiles);                       // about one work item per SM
+  int c = ceil_div(ceil_div(M, s), tc::BKF) * tc::BKF;
+  if (c < 8 * tc::BKF) c = 8 * tc::BKF;               // >= 256 reduction rows per item: amortise the 64 KB tile drain
+  s = ceil_div(M, c);
+  if (s < 1) s = 1;
+  *splits = s;
+  *chunk = c;
+}
+
+bool tc_dw_eligible(const GemmDW& q) {
+  return q.M >= 2048 && q.Nn >= 32 && q.Kk >= 32 && (q.ldg % 4) == 0 && (q.ldx % 4) == 0 &&
+         (reinterpret_cast<uintptr_t>(q.G) & 15) == 0 && (reinterpret_cast<uintptr_t>(q.X) & 15) == 0;
+}
+
+// partial products into q.scratch ([splits][Nn][Kk]); the caller reduces them (reduce_dw_kernel)
+int gemm_dw_tc_partials(const GemmDW& q, int* splits_out, cudaStream_t st) {
+  using namespace tc;
+  static int num_sms = 0;
+  static bool attr_done = false;
+  if (!attr_done) {
+    int dev = 0;
+    GIB_CUDA_TRY(cudaGetDevice(&dev));
+    GIB_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    GIB_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_nt_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    GIB_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_nt_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_done = true;
+  }
+  int splits, chunk;
+  tc_dw_plan(q.M, q.Nn, q.Kk, &splits, &chunk);
+  CUtensorMap ma, mb;
+  GIB_TRY(make_map(&ma, q.G, q.M, q.Nn, q.ldg, BKF, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));   // boxes: 32 floats x 32 rows
+  GIB_TRY(make_map(&mb, q.X, q.M, q.Kk, q.ldx, BKF, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+  Params P;
+  P.g = GemmNT();
+  P.g.C = q.scratch; P.g.ldc = q.Kk; P.g.M = q.Nn; P.g.N = q.Kk; P.g.n_store = q.Kk; P.g.n_valid = q.Kk;
+  P.g.mode = EPI_ACT; P.g.act = ACT_NONE; P.g.bias = nullptr;
+  P.m_tiles = ceil_div(q.Nn, BM);
+  P.n_tiles = ceil_div(q.Kk, BN);
+  P.k_blocks = 0;
+  P.tn = 1; P.splits = splits; P.chunk_rows = chunk; P.tn_rows = q.M; P.tn_nn = q.Nn; P.tn_kk = q.Kk;
+  P.debug = g_tc_debug;
+  const int items = P.m_tiles * P.n_tiles * splits;
+  const int grid = items < num_sms ? items : num_sms;
+  if (g_tc_debug & 4) tc_gemm_nt_kernel<0><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, P);
+  else tc_gemm_nt_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, P);
+  GIB_LAUNCH_CHECK();
+  *splits_out = splits;
   return 0;
 }
 
