@@ -312,29 +312,60 @@ __global__ void __launch_bounds__(256, 2) sgemm_tn_splitk_kernel(const GemmTN p)
     }
 }
 
-// out[(r)*rs + c*cs] (+)= sum_z ws[z][prow(r)][c]   with prow(r) = (r / Rb) * Rbp + r % Rb
-__global__ void reduce_dw_kernel(const float* __restrict__ ws, int splits, int Nn, int Kk,
-                                 float* __restrict__ out, int R, int C, int Rb, int Rbp,
-                                 long long rs, long long cs) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)R * C) return;
-  const int r = (int)(idx / C), c = (int)(idx % C);
-  const int prow = (r / Rb) * Rbp + (r % Rb);
-  const float* src = ws + (size_t)prow * Kk + c;
-  const size_t stride = (size_t)Nn * Kk;
-  float s = 0.f;
-  for (int zi = 0; zi < splits; ++zi) s += src[zi * stride];
-  out[r * rs + c * cs] += s;
+// Fixed-order reduction of the split partials into the gradient tensors, one launch for weight AND bias:
+//   blocks [0, nblk_w):  dW[r*rs + c*cs] += sum_z ws[z][prow(r)][c]      (one thread per element, z ascending)
+//   blocks [nblk_w, ..): db[r]           += sum_z wsb[z][prow(r)]        (32 rows per block, 8 partial chains)
+// prow(r) = (r / Rb) * Rbp + r % Rb maps a real row to its padded (gate-blocked) row.
+__global__ void __launch_bounds__(256) reduce_grads_kernel(const float* __restrict__ ws, int splits, int Nn, int Kk,
+                                                           float* __restrict__ dW, int R, int C, int Rb, int Rbp,
+                                                           long long rs, long long cs, int nblk_w,
+                                                           const float* __restrict__ wsb, int bsplits,
+                                                           float* __restrict__ db) {
+  if ((int)blockIdx.x < nblk_w) {
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= (long long)R * C) return;
+    const int r = (int)(idx / C), c = (int)(idx % C);
+    const int prow = (r / Rb) * Rbp + (r % Rb);
+    const float* src = ws + (size_t)prow * Kk + c;
+    const size_t stride = (size_t)Nn * Kk;
+    float s = 0.f;
+    int zi = 0;
+    for (; zi + 8 <= splits; zi += 8) {      // 8 independent loads in flight, summed in ascending z
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = src[(size_t)(zi + u) * stride];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s += v[u];
+    }
+    for (; zi < splits; ++zi) s += src[(size_t)zi * stride];
+    dW[r * rs + c * cs] += s;
+  } else {
+    __shared__ float sm[8][33];
+    const int r = ((int)blockIdx.x - nblk_w) * 32 + (threadIdx.x & 31);
+    const int wy = threadIdx.x >> 5;
+    float s = 0.f;
+    if (r < R) {
+      const int prow = (r / Rb) * Rbp + (r % Rb);
+      for (int zi = wy; zi < bsplits; zi += 8) s += wsb[(size_t)zi * Nn + prow];
+    }
+    sm[wy][threadIdx.x & 31] = s;
+    __syncthreads();
+    if (wy == 0 && r < R) {
+      float t = 0.f;
+      for (int k = 0; k < 8; ++k) t += sm[k][threadIdx.x];
+      db[r] += t;
+    }
+  }
 }
 
-__global__ void reduce_db_kernel(const float* __restrict__ wsb, int splits, int Nn,
-                                 float* __restrict__ out, int R, int Rb, int Rbp) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= R) return;
-  const int prow = (r / Rb) * Rbp + (r % Rb);
-  float s = 0.f;
-  for (int zi = 0; zi < splits; ++zi) s += wsb[(size_t)zi * Nn + prow];
-  out[r] += s;
+static int launch_reduce(const float* ws, int splits, const GemmDW& q, const float* wsb, int bsplits, cudaStream_t st) {
+  const int nblk_w = q.dW ? (int)ceil_div_ll((long long)q.R * q.C, 256) : 0;
+  const int nblk_b = q.dbias ? ceil_div(q.R, 32) : 0;
+  if (nblk_w + nblk_b == 0) return 0;
+  reduce_grads_kernel<<<nblk_w + nblk_b, 256, 0, st>>>(ws, splits, q.Nn, q.Kk, q.dW, q.R, q.C, q.Rb, q.Rbp, q.rs, q.cs,
+                                                      nblk_w, wsb, bsplits, q.dbias);
+  GIB_LAUNCH_CHECK();
+  return 0;
 }
 
 // part[z][n] = sum over the z-th row chunk of G[m, n]  (fixed order inside the chunk; chunks reduced in order)
@@ -391,18 +422,12 @@ int gemm_dw(const GemmDW& q, cudaStream_t st) {
     // fixed-order split reduction; the bias gradient is a separate column sum of G
     int tsplits = 0;
     GIB_TRY(gemm_dw_tc_partials(q, &tsplits, st));
-    const long long tot = (long long)q.R * q.C;
-    reduce_dw_kernel<<<(unsigned)ceil_div_ll(tot, 256), 256, 0, st>>>(q.scratch, tsplits, q.Nn, q.Kk, q.dW, q.R, q.C,
-                                                                     q.Rb, q.Rbp, q.rs, q.cs);
-    GIB_LAUNCH_CHECK();
+    float* part = q.scratch + (size_t)tsplits * q.Nn * q.Kk;       // [kColsumSplits][Nn] partial column sums
     if (q.dbias) {
-      float* part = q.scratch + (size_t)tsplits * q.Nn * q.Kk;     // [kColsumSplits][Nn] partial column sums
       colsum_partial_kernel<<<dim3(ceil_div(q.Nn, 32), kColsumSplits), 256, 0, st>>>(part, q.G, q.ldg, q.M, q.Nn);
       GIB_LAUNCH_CHECK();
-      reduce_db_kernel<<<ceil_div(q.R, 256), 256, 0, st>>>(part, kColsumSplits, q.Nn, q.dbias, q.R, q.Rb, q.Rbp);
-      GIB_LAUNCH_CHECK();
     }
-    return 0;
+    return launch_reduce(q.scratch, tsplits, q, part, kColsumSplits, st);
   }
   int splits, chunk;
   gemm_dw_plan(q.M, q.Nn, q.Kk, &splits, &chunk);
@@ -415,23 +440,14 @@ int gemm_dw(const GemmDW& q, cudaStream_t st) {
     dim3 grid(ceil_div(q.Kk, 128), ceil_div(q.Nn, 128), splits);
     sgemm_tn_splitk_kernel<128, 128, 2, 2><<<grid, 256, 0, st>>>(p);
     GIB_LAUNCH_CHECK();
-    const long long tot = (long long)q.R * q.C;
-    reduce_dw_kernel<<<(unsigned)ceil_div_ll(tot, 256), 256, 0, st>>>(p.ws, splits, q.Nn, q.Kk, q.dW, q.R, q.C,
-                                                                     q.Rb, q.Rbp, q.rs, q.cs);
+  } else if (q.dbias) {  // bias only: run one k-tile column
+    GemmTN pb = p;
+    pb.Kk = 4;  // minimal X extent; acc discarded (the ws slab holds >= Nn*4 floats per split: Kk >= 16 everywhere)
+    dim3 grid(1, ceil_div(q.Nn, 128), splits);
+    sgemm_tn_splitk_kernel<128, 128, 2, 2><<<grid, 256, 0, st>>>(pb);
     GIB_LAUNCH_CHECK();
   }
-  if (q.dbias) {
-    if (!q.dW) {  // bias only: run one k-tile column
-      GemmTN pb = p;
-      pb.Kk = 4;  // minimal X extent; acc discarded
-      dim3 grid(1, ceil_div(q.Nn, 128), splits);
-      // ws slab must still hold Nn*4 floats per split: it does (Kk >= 16 in every caller)
-      sgemm_tn_splitk_kernel<128, 128, 2, 2><<<grid, 256, 0, st>>>(pb);
-      GIB_LAUNCH_CHECK();
-    }
-    reduce_db_kernel<<<ceil_div(q.R, 256), 256, 0, st>>>(p.ws_bias, splits, q.Nn, q.dbias, q.R, q.Rb, q.Rbp);
-    GIB_LAUNCH_CHECK();
-  }
+  GIB_TRY(launch_reduce(p.ws, splits, q, p.ws_bias, splits, st));
   return 0;
 }
 

@@ -511,7 +511,7 @@ bool tc_dw_eligible(const GemmDW& q) {
          (reinterpret_cast<uintptr_t>(q.G) & 15) == 0 && (reinterpret_cast<uintptr_t>(q.X) & 15) == 0;
 }
 
-// partial products into q.scratch ([splits][Nn][Kk]); the caller reduces them (reduce_dw_kernel)
+// partial products into q.scratch ([splits][Nn][Kk]); the caller reduces them (reduce_grads_kernel)
 int gemm_dw_tc_partials(const GemmDW& q, int* splits_out, cudaStream_t st) {
   using namespace tc;
   static int num_sms = 0;
