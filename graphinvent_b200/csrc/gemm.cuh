@@ -52,6 +52,8 @@ struct GemmDW {
 int gemm_nt(const GemmNT& p, cudaStream_t st);      // dispatches to the tcgen05 path when enabled and eligible
 int gemm_nt_simt(const GemmNT& p, cudaStream_t st);
 int gemm_nt_tc(const GemmNT& p, cudaStream_t st);
+int gemm_nt_tc_group(const GemmNT* ps, int n, cudaStream_t st);   // n <= 4 independent problems, one launch
+int gemm_nt_group(const GemmNT* ps, int n, cudaStream_t st);      // dispatcher: grouped tcgen05 launch or per-problem
 bool tc_eligible(const GemmNT& p);
 extern bool g_use_tc;
 extern int g_tc_debug;

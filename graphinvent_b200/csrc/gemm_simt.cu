@@ -170,6 +170,22 @@ int gemm_nt(const GemmNT& p, cudaStream_t st) {
   return gemm_nt_simt(p, st);
 }
 
+// Several independent problems (sibling MLPs, the per-bond-type message MLPs): one grouped tensor-core launch when
+// together they fill the machine reasonably, else problem by problem.
+int gemm_nt_group(const GemmNT* ps, int n, cudaStream_t st) {
+  if (n == 1) return gemm_nt(ps[0], st);
+  bool ok = g_use_tc && n <= 4;
+  long long tiles = 0;
+  for (int i = 0; i < n && ok; ++i) {
+    if (ps[i].M <= 0 || ps[i].N <= 0) continue;
+    ok = tc_eligible(ps[i]) && ps[i].K >= 32 && ps[i].N >= 48;
+    tiles += (long long)ceil_div(ps[i].M, 128) * ceil_div(ps[i].N, 128);
+  }
+  if (ok && tiles >= 16) return gemm_nt_tc_group(ps, n, st);
+  for (int i = 0; i < n; ++i) GIB_TRY(gemm_nt(ps[i], st));
+  return 0;
+}
+
 int gemm_nt_simt(const GemmNT& p, cudaStream_t st) {
   if (p.M <= 0 || p.N <= 0) return 0;
   if (p.K % BK != 0 || (p.lda & 3) || (p.ldb & 3) || p.K <= 0) {

@@ -16,6 +16,7 @@
 //                                 coalesced global stores (two warps per TMEM lane quarter)
 // Every mbarrier wait is bounded: a dead-lock turns into a trap (error at the next API call), never a hang.
 #include <cuda.h>
+#include <string.h>
 
 #include "gemm.cuh"
 
@@ -153,19 +154,51 @@ __device__ __forceinline__ float act_fast(float x, int act) {
   return x;
 }
 
+constexpr int MAXP = 4;   // independent GEMM problems per launch (grouped NT launches)
+
+struct Maps {   // TMA descriptors live in kernel-parameter space (__grid_constant__)
+  CUtensorMap a[MAXP];
+  CUtensorMap b[MAXP];
+};
+
 struct Params {
-  GemmNT g;
-  int m_tiles, n_tiles, k_blocks;
+  // NT mode: up to MAXP independent problems C_p = epi(A_p B_p^T) share one persistent launch; work items are their
+  // output tiles, concatenated (tile_begin[p] .. tile_begin[p+1]).  Used for the per-bond-type message MLPs (same
+  // layer, different weights and row ranges) and for sibling MLPs of the readout.
+  GemmNT g[MAXP];
+  int m_tiles[MAXP], n_tiles[MAXP], k_blocks[MAXP], tile_begin[MAXP + 1];
+  int nprob;
   // TN (weight-gradient) mode: P[z][n][k] = sum_{m in chunk z} G[m,n] X[m,k]; operands are the row-major
-  // activations themselves (MN-major for the MMA), g.A = G, g.B = X, g.C = split-K workspace
+  // activations themselves (MN-major for the MMA), problem 0 only, g[0].C = split-K workspace
   int tn, splits, chunk_rows, tn_rows, tn_nn, tn_kk;
   int debug;   // bit0: skip the hi/lo split (timing experiments only), bit1: skip the epilogue stores
 };
 
+struct Item { int p, m0, n0, nkb, z; };
+
+__device__ __forceinline__ Item decode_item(const Params& P, int item) {
+  Item it;
+  if (P.tn) {
+    const int tiles_mn = P.m_tiles[0] * P.n_tiles[0];
+    const int tile = item % tiles_mn;
+    it.p = 0; it.z = item / tiles_mn;
+    it.m0 = (tile / P.n_tiles[0]) * BM; it.n0 = (tile % P.n_tiles[0]) * BN;
+    const int r0 = it.z * P.chunk_rows;
+    it.nkb = ceil_div(min(P.tn_rows, r0 + P.chunk_rows) - r0, BKF);
+  } else {
+    int p = 0;
+    while (p + 1 < P.nprob && item >= P.tile_begin[p + 1]) ++p;
+    const int tile = item - P.tile_begin[p];
+    it.p = p; it.z = 0;
+    it.m0 = (tile / P.n_tiles[p]) * BM; it.n0 = (tile % P.n_tiles[p]) * BN;
+    it.nkb = P.k_blocks[p];
+  }
+  return it;
+}
+
 template <int SPLIT>   // 0: hi = truncation, lo = exact remainder;  1: hi, lo both round-to-nearest (cvt.rna)
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                  const Params P) {
+tc_gemm_nt_kernel(const __grid_constant__ Maps maps, const Params P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -177,9 +210,8 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const GemmNT& g = P.g;
-  const int tiles_mn = P.m_tiles * P.n_tiles;
-  const int num_tiles = tiles_mn * (P.tn ? P.splits : 1);   // TN: one work item per (tile, reduction chunk)
+  // work items: NT = output tiles of all problems; TN = (output tile, reduction chunk) pairs
+  const int num_tiles = P.tn ? P.m_tiles[0] * P.n_tiles[0] * P.splits : P.tile_begin[P.nprob];
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -209,23 +241,24 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
-        const int tile = item % tiles_mn, z = item / tiles_mn;
-        const int m0 = (tile / P.n_tiles) * BM, n0 = (tile % P.n_tiles) * BN;
-        const int r0 = z * P.chunk_rows;
-        const int nkb = P.tn ? ceil_div(min(P.tn_rows, r0 + P.chunk_rows) - r0, BKF) : P.k_blocks;
+        const Item w = decode_item(P, item);
+        const CUtensorMap* map_a = &maps.a[w.p];
+        const CUtensorMap* map_b = &maps.b[w.p];
+        const int m0 = w.m0, n0 = w.n0, nkb = w.nkb;
+        const int r0 = w.z * P.chunk_rows;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* st = smem + stage * STAGE_BYTES;
           mbar_arrive_expect_tx(&full_raw[stage], 2 * TILE_BYTES);
           if (!P.tn) {
-            tma_load_2d(&map_a, &full_raw[stage], st, kb * BKF, m0);
-            tma_load_2d(&map_b, &full_raw[stage], st + 2 * TILE_BYTES, kb * BKF, n0);
+            tma_load_2d(map_a, &full_raw[stage], st, kb * BKF, m0);
+            tma_load_2d(map_b, &full_raw[stage], st + 2 * TILE_BYTES, kb * BKF, n0);
           } else {
             const int row = r0 + kb * BKF;           // 32 reduction rows per stage
 #pragma unroll
             for (int j = 0; j < 4; ++j) {            // four 32-float column groups per operand
-              tma_load_2d(&map_a, &full_raw[stage], st + j * 4096, m0 + 32 * j, row);
-              tma_load_2d(&map_b, &full_raw[stage], st + 2 * TILE_BYTES + j * 4096, n0 + 32 * j, row);
+              tma_load_2d(map_a, &full_raw[stage], st + j * 4096, m0 + 32 * j, row);
+              tma_load_2d(map_b, &full_raw[stage], st + 2 * TILE_BYTES + j * 4096, n0 + 32 * j, row);
             }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -239,9 +272,7 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       uint32_t phase = 0;
       int it = 0;
       for (int item = blockIdx.x; item < num_tiles; item += gridDim.x, ++it) {
-        const int z = item / tiles_mn;
-        const int r0 = z * P.chunk_rows;
-        const int nkb = P.tn ? ceil_div(min(P.tn_rows, r0 + P.chunk_rows) - r0, BKF) : P.k_blocks;
+        const int nkb = decode_item(P, item).nkb;
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);
@@ -287,8 +318,7 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     int stage = 0;
     uint32_t phase = 0;
     for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
-      const int r0s = (item / tiles_mn) * P.chunk_rows;
-      const int nkb = P.tn ? ceil_div(min(P.tn_rows, r0s + P.chunk_rows) - r0s, BKF) : P.k_blocks;
+      const int nkb = decode_item(P, item).nkb;
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(&full_raw[stage], phase);
         uint8_t* st = smem + stage * STAGE_BYTES;
@@ -332,15 +362,16 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int half = (warp - 6) >> 2;          // which 64-column half of the tile this warp drains
     float* stg = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256) + (warp - 6) * (32 * EPI_LD);
     const int rr = lane >> 2, cc = (lane & 3) * 4;
-    const bool vec_c = (g.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
-    const bool vec_x = g.aux && (g.ldaux & 3) == 0 && ((reinterpret_cast<uintptr_t>(g.aux) & 15) == 0);
     int it = 0;
     for (int item = blockIdx.x; item < num_tiles; item += gridDim.x, ++it) {
-      const int tile = item % tiles_mn;
-      float* const Cbase = g.C + (P.tn ? (size_t)(item / tiles_mn) * P.tn_nn * P.tn_kk : (size_t)0);
+      const Item w = decode_item(P, item);
+      const GemmNT& g = P.g[w.p];
+      const bool vec_c = (g.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
+      const bool vec_x = g.aux && (g.ldaux & 3) == 0 && ((reinterpret_cast<uintptr_t>(g.aux) & 15) == 0);
+      float* const Cbase = g.C + (P.tn ? (size_t)w.z * P.tn_nn * P.tn_kk : (size_t)0);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int m0 = (tile / P.n_tiles) * BM, n0 = (tile % P.n_tiles) * BN;
+      const int m0 = w.m0, n0 = w.n0;
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
@@ -460,10 +491,8 @@ bool tc_eligible(const GemmNT& p) {
          (reinterpret_cast<uintptr_t>(p.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.B) & 15) == 0;
 }
 
-int gemm_nt_tc(const GemmNT& p, cudaStream_t st) {
+static int tc_prepare(int* num_sms_out) {
   using namespace tc;
-  if (p.M <= 0 || p.N <= 0) return 0;
-  if (!tc_eligible(p)) { set_error("gemm_nt_tc: operands violate the TMA alignment contract"); return -2; }
   static int num_sms = 0;
   static bool attr_done = false;
   if (!attr_done) {
@@ -474,25 +503,50 @@ int gemm_nt_tc(const GemmNT& p, cudaStream_t st) {
     GIB_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_nt_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_done = true;
   }
-  CUtensorMap ma, mb;
-  GIB_TRY(make_map(&ma, p.A, p.M, p.K, p.lda));
-  GIB_TRY(make_map(&mb, p.B, p.N, p.K, p.ldb));
+  *num_sms_out = num_sms;
+  return 0;
+}
+
+// up to MAXP independent NT problems in one persistent launch
+int gemm_nt_tc_group(const GemmNT* ps, int n, cudaStream_t st) {
+  using namespace tc;
+  if (n < 1 || n > MAXP) { set_error("gemm_nt_tc_group: %d problems (max %d)", n, MAXP); return -2; }
+  int num_sms = 0;
+  GIB_TRY(tc_prepare(&num_sms));
+  Maps maps;
   Params P;
-  P.g = p;
-  P.m_tiles = ceil_div(p.M, BM);
-  P.n_tiles = ceil_div(p.N, BN);
-  P.k_blocks = ceil_div(p.K, BKF);
-  P.tn = 0; P.splits = 1; P.chunk_rows = 0; P.tn_rows = 0; P.tn_nn = 0; P.tn_kk = 0;
+  memset(&P, 0, sizeof(P));
+  double work = 0;
+  int tiles = 0, np = 0;
+  for (int i = 0; i < n; ++i) {
+    const GemmNT& p = ps[i];
+    if (p.M <= 0 || p.N <= 0) continue;
+    if (!tc_eligible(p)) { set_error("gemm_nt_tc: operands violate the TMA alignment contract"); return -2; }
+    GIB_TRY(make_map(&maps.a[np], p.A, p.M, p.K, p.lda));
+    GIB_TRY(make_map(&maps.b[np], p.B, p.N, p.K, p.ldb));
+    P.g[np] = p;
+    P.m_tiles[np] = ceil_div(p.M, BM);
+    P.n_tiles[np] = ceil_div(p.N, BN);
+    P.k_blocks[np] = ceil_div(p.K, BKF);
+    P.tile_begin[np] = tiles;
+    tiles += P.m_tiles[np] * P.n_tiles[np];
+    work += p.work > 0 ? p.work : 2.0 * p.M * (double)p.N * p.K;
+    ++np;
+  }
+  if (np == 0) return 0;
+  for (int i = np; i <= MAXP; ++i) P.tile_begin[i] = tiles;
+  P.nprob = np;
   P.debug = g_tc_debug;
-  const int tiles = P.m_tiles * P.n_tiles;
   const int grid = tiles < num_sms ? tiles : num_sms;
-  ProfScope prof(PROF_GEMM_NT, p.work > 0 ? p.work : 2.0 * p.M * (double)p.N * p.K, st);
+  ProfScope prof(PROF_GEMM_NT, work, st);
   // default: round-to-nearest split (same speed -- the splitters are smem-bound -- and ~30% smaller error)
-  if (g_tc_debug & 4) tc_gemm_nt_kernel<0><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, P);
-  else tc_gemm_nt_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, P);
+  if (g_tc_debug & 4) tc_gemm_nt_kernel<0><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps, P);
+  else tc_gemm_nt_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps, P);
   GIB_LAUNCH_CHECK();
   return 0;
 }
+
+int gemm_nt_tc(const GemmNT& p, cudaStream_t st) { return gemm_nt_tc_group(&p, 1, st); }
 
 // ---- weight-gradient GEMM on the tensor cores --------------------------------------------------------------
 void tc_dw_plan(int M, int Nn, int Kk, int* splits, int* chunk) {
@@ -514,34 +568,28 @@ bool tc_dw_eligible(const GemmDW& q) {
 // partial products into q.scratch ([splits][Nn][Kk]); the caller reduces them (reduce_grads_kernel)
 int gemm_dw_tc_partials(const GemmDW& q, int* splits_out, cudaStream_t st) {
   using namespace tc;
-  static int num_sms = 0;
-  static bool attr_done = false;
-  if (!attr_done) {
-    int dev = 0;
-    GIB_CUDA_TRY(cudaGetDevice(&dev));
-    GIB_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    GIB_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_nt_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    GIB_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_nt_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_done = true;
-  }
+  int num_sms = 0;
+  GIB_TRY(tc_prepare(&num_sms));
   int splits, chunk;
   tc_dw_plan(q.M, q.Nn, q.Kk, &splits, &chunk);
-  CUtensorMap ma, mb;
-  GIB_TRY(make_map(&ma, q.G, q.M, q.Nn, q.ldg, BKF, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));   // boxes: 32 floats x 32 rows
-  GIB_TRY(make_map(&mb, q.X, q.M, q.Kk, q.ldx, BKF, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+  Maps maps;
+  GIB_TRY(make_map(&maps.a[0], q.G, q.M, q.Nn, q.ldg, BKF, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));   // 32 floats x 32 rows
+  GIB_TRY(make_map(&maps.b[0], q.X, q.M, q.Kk, q.ldx, BKF, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
   Params P;
-  P.g = GemmNT();
-  P.g.C = q.scratch; P.g.ldc = q.Kk; P.g.M = q.Nn; P.g.N = q.Kk; P.g.n_store = q.Kk; P.g.n_valid = q.Kk;
-  P.g.mode = EPI_ACT; P.g.act = ACT_NONE; P.g.bias = nullptr;
-  P.m_tiles = ceil_div(q.Nn, BM);
-  P.n_tiles = ceil_div(q.Kk, BN);
-  P.k_blocks = 0;
+  memset(&P, 0, sizeof(P));
+  GemmNT& g = P.g[0];
+  g = GemmNT();
+  g.C = q.scratch; g.ldc = q.Kk; g.M = q.Nn; g.N = q.Kk; g.n_store = q.Kk; g.n_valid = q.Kk;
+  g.mode = EPI_ACT; g.act = ACT_NONE; g.bias = nullptr;
+  P.m_tiles[0] = ceil_div(q.Nn, BM);
+  P.n_tiles[0] = ceil_div(q.Kk, BN);
+  P.nprob = 1;
   P.tn = 1; P.splits = splits; P.chunk_rows = chunk; P.tn_rows = q.M; P.tn_nn = q.Nn; P.tn_kk = q.Kk;
   P.debug = g_tc_debug;
-  const int items = P.m_tiles * P.n_tiles * splits;
+  const int items = P.m_tiles[0] * P.n_tiles[0] * splits;
   const int grid = items < num_sms ? items : num_sms;
-  if (g_tc_debug & 4) tc_gemm_nt_kernel<0><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, P);
-  else tc_gemm_nt_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, P);
+  if (g_tc_debug & 4) tc_gemm_nt_kernel<0><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps, P);
+  else tc_gemm_nt_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps, P);
   GIB_LAUNCH_CHECK();
   *splits_out = splits;
   return 0;

@@ -331,6 +331,125 @@ static int mlp_backward(const Run& r, const BwdBufs& bb, const Mlp& m, const flo
   return 0;
 }
 
+// ---- several MLPs of equal depth advanced layer by layer, each layer as ONE grouped GEMM launch --------------
+struct MlpJob {
+  const Mlp* m; const float* X0; const MlpAct* a; long long row0; int rows;
+  float* ext_out; int ext_ld, ext_valid;
+};
+struct MlpBwdJob {
+  const Mlp* m; const float* X0; const MlpAct* a; long long row0; int rows;
+  const float* Gtop; float* dX0; int ld_dx; const float* dx_aux;
+};
+
+static size_t mlp_max_ld(const Plan& pl, const Mlp& m) {
+  size_t w = 16;
+  for (int l = 0; l < m.n; ++l) w = std::max(w, (size_t)std::max(pl.lins[m.first + l].Rp, pl.lins[m.first + l].Cp));
+  return w;
+}
+
+static int mlp_forward_multi(const Run& r, const MlpJob* jobs, int n) {
+  bool same = n <= 4;
+  for (int i = 1; i < n && same; ++i) same = jobs[i].m->n == jobs[0].m->n;
+  if (!same) {
+    for (int i = 0; i < n; ++i)
+      GIB_TRY(mlp_forward(r, *jobs[i].m, jobs[i].X0, *jobs[i].a, jobs[i].row0, jobs[i].rows, jobs[i].ext_out,
+                          jobs[i].ext_ld, jobs[i].ext_valid));
+    return 0;
+  }
+  const float* x[4]; int ldx[4];
+  for (int i = 0; i < n; ++i) { x[i] = jobs[i].X0 + (size_t)jobs[i].row0 * jobs[i].a->ld[0]; ldx[i] = jobs[i].a->ld[0]; }
+  for (int l = 1; l <= jobs[0].m->n; ++l) {
+    GemmNT ps[4];
+    int np = 0, idx[4];
+    for (int i = 0; i < n; ++i) {
+      const MlpJob& j = jobs[i];
+      if (j.rows <= 0) continue;
+      const Lin& L = r.pl.lins[j.m->first + l - 1];
+      GemmNT& p = ps[np];
+      p = GemmNT();
+      p.A = x[i]; p.lda = ldx[i];
+      p.B = r.packed + L.ow; p.ldb = L.Cp;
+      p.M = j.rows; p.N = L.Rp; p.K = L.Cp;
+      p.bias = L.pb >= 0 ? r.packed + L.ob : nullptr;
+      p.act = j.m->act; p.mode = EPI_ACT;
+      p.work = 2.0 * j.rows * (double)L.R * L.C;
+      if (l == j.m->n && j.ext_out) {
+        p.C = j.ext_out + (size_t)j.row0 * j.ext_ld; p.ldc = j.ext_ld; p.n_store = j.ext_valid; p.n_valid = j.ext_valid;
+      } else {
+        p.C = r.ws + j.a->y[l] + (size_t)j.row0 * j.a->ld[l]; p.ldc = j.a->ld[l]; p.n_store = L.Rp; p.n_valid = L.Rp;
+      }
+      if (ldx[i] < L.Cp) { set_error("mlp_forward_multi: input ld %d < padded K %d", ldx[i], L.Cp); return -2; }
+      idx[np++] = i;
+    }
+    GIB_TRY(gemm_nt_group(ps, np, r.st));
+    for (int k = 0; k < np; ++k) { x[idx[k]] = ps[k].C; ldx[idx[k]] = ps[k].ldc; }
+  }
+  return 0;
+}
+
+static int mlp_backward_multi(const Run& r, const BwdBufs& bb, const MlpBwdJob* jobs, int n) {
+  bool same = n <= 4;
+  for (int i = 1; i < n && same; ++i) same = jobs[i].m->n == jobs[0].m->n;
+  if (!same || n == 1) {
+    for (int i = 0; i < n; ++i)
+      GIB_TRY(mlp_backward(r, bb, *jobs[i].m, jobs[i].X0, *jobs[i].a, jobs[i].row0, jobs[i].rows, jobs[i].Gtop,
+                           jobs[i].dX0, jobs[i].ld_dx, jobs[i].dx_aux));
+    return 0;
+  }
+  const float* G[4]; float* ping[4]; float* pong[4];
+  size_t off = 0;
+  for (int i = 0; i < n; ++i) {   // private ping/pong slice per job inside GA / GB
+    G[i] = jobs[i].Gtop;
+    ping[i] = r.scratch + bb.GA + off;
+    pong[i] = r.scratch + bb.GB + off;
+    off += ((size_t)std::max(jobs[i].rows, 0) * mlp_max_ld(r.pl, *jobs[i].m) + 31) & ~(size_t)31;
+  }
+  for (int l = jobs[0].m->n; l >= 1; --l) {
+    GemmNT ps[4];
+    int np = 0, idx[4];
+    for (int i = 0; i < n; ++i) {
+      const MlpBwdJob& j = jobs[i];
+      if (j.rows <= 0) continue;
+      const Lin& L = r.pl.lins[j.m->first + l - 1];
+      const float* Xin = (l == 1) ? j.X0 + (size_t)j.row0 * j.a->ld[0]
+                                  : r.ws + j.a->y[l - 1] + (size_t)j.row0 * j.a->ld[l - 1];
+      const int ldxin = j.a->ld[l - 1];
+      GemmDW q;
+      q.G = G[i]; q.ldg = L.Rp; q.Nn = L.Rp; q.X = Xin; q.ldx = ldxin; q.Kk = L.Cp; q.M = j.rows;
+      q.dW = r.grads[L.pw] + L.src_off;
+      q.dbias = L.pb >= 0 ? r.grads[L.pb] : nullptr;
+      q.R = L.R; q.C = L.C; q.Rb = L.Rb; q.Rbp = L.Rbp; q.rs = L.rs; q.cs = L.cs;
+      q.scratch = r.scratch + bb.dw;
+      q.work = 2.0 * j.rows * (double)L.R * L.C;
+      GIB_TRY(gemm_dw(q, r.st));
+      if (l > 1) {
+        GemmNT& p = ps[np];
+        p = GemmNT();
+        p.A = G[i]; p.lda = L.Rp; p.B = r.packed + L.owt; p.ldb = L.Rp;
+        p.M = j.rows; p.N = L.Ctp; p.K = L.Rp; p.n_store = L.Ctp; p.n_valid = L.Ctp;
+        p.work = 2.0 * j.rows * (double)L.R * L.Ct;
+        p.C = (G[i] == ping[i]) ? pong[i] : ping[i]; p.ldc = L.Ctp;
+        p.mode = EPI_MUL_DACT; p.act = j.m->act; p.aux = Xin; p.ldaux = ldxin;
+        idx[np++] = i;
+      } else if (j.dX0) {   // input gradients may chain through a shared buffer (aux): keep them in order
+        GemmNT p1;
+        p1.A = G[i]; p1.lda = L.Rp; p1.B = r.packed + L.owt; p1.ldb = L.Rp;
+        p1.M = j.rows; p1.N = L.Ctp; p1.K = L.Rp; p1.n_store = L.Ctp; p1.n_valid = L.Ctp;
+        p1.work = 2.0 * j.rows * (double)L.R * L.Ct;
+        p1.C = j.dX0; p1.ldc = j.ld_dx;
+        if (j.dx_aux) { p1.mode = EPI_ADD; p1.aux = j.dx_aux; p1.ldaux = j.ld_dx; }
+        else { p1.mode = EPI_ACT; p1.act = ACT_NONE; p1.bias = nullptr; }
+        GIB_TRY(gemm_nt(p1, r.st));
+      }
+    }
+    if (np) {
+      GIB_TRY(gemm_nt_group(ps, np, r.st));
+      for (int k = 0; k < np; ++k) G[idx[k]] = ps[k].C;
+    }
+  }
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------
 // readout (GraphGather / sum + GlobalReadout)
 // ------------------------------------------------------------------------------------
@@ -347,21 +466,30 @@ static int readout_forward(const Run& r, float* out) {
     const int ldc = L.gatt.ld[0];
     if (d.model == GIB_EMN) GIB_TRY(concat2(r.ws + L.cat_att, ldc, hT, Hp, d.H, hT, Hp, d.H, S, r.st));
     else GIB_TRY(concat2(r.ws + L.cat_att, ldc, hT, Hp, d.H, r.nodes, d.F, d.F, S, r.st));  // modules.py:46
-    GIB_TRY(mlp_forward(r, pl.gatt, r.ws + L.cat_att, L.gatt, 0, (int)S));
-    GIB_TRY(mlp_forward(r, pl.gemb, hT, L.gemb, 0, (int)S));
+    {   // att_nn(cat) and emb_nn(hidden) are independent: one grouped launch per layer
+      MlpJob jobs[2] = {{&pl.gatt, r.ws + L.cat_att, &L.gatt, 0, (int)S, nullptr, 0, 0},
+                        {&pl.gemb, hT, &L.gemb, 0, (int)S, nullptr, 0, 0}};
+      GIB_TRY(mlp_forward_multi(r, jobs, 2));
+    }
     GIB_TRY(graph_gather_fwd(r.ws + L.g, r.ws + L.attn, r.ws + L.gatt.y[pl.gatt.n], r.ws + L.gemb.y[pl.gemb.n], Gp,
                              r.ga.dst_ptr, d.N, d.B, d.big, r.st));                   // modules.py:47-52
   }
-  GIB_TRY(mlp_forward(r, pl.fadd1, hT, L.fadd1, 0, (int)S));                          // modules.py:250
-  GIB_TRY(mlp_forward(r, pl.fconn1, hT, L.fconn1, 0, (int)S));                        // modules.py:251
+  {   // modules.py:250-251: the two tier-1 heads share their input
+    MlpJob jobs[2] = {{&pl.fadd1, hT, &L.fadd1, 0, (int)S, nullptr, 0, 0},
+                      {&pl.fconn1, hT, &L.fconn1, 0, (int)S, nullptr, 0, 0}};
+    GIB_TRY(mlp_forward_multi(r, jobs, 2));
+  }
   GIB_TRY(concat_flat(r.ws + L.cat_add, L.fadd2.ld[0], r.ws + L.fadd1.y[pl.fadd1.n], L.fadd1.ld[pl.fadd1.n], d.N,
                       d.f_add, r.ws + L.g, Gp, pl.G, d.B, r.st));
   GIB_TRY(concat_flat(r.ws + L.cat_conn, L.fconn2.ld[0], r.ws + L.fconn1.y[pl.fconn1.n], L.fconn1.ld[pl.fconn1.n],
                       d.N, d.f_conn, r.ws + L.g, Gp, pl.G, d.B, r.st));
   const int na = d.N * d.f_add, nc = d.N * d.f_conn;
-  GIB_TRY(mlp_forward(r, pl.fadd2, r.ws + L.cat_add, L.fadd2, 0, d.B, out, pl.apd, na));          // :270
-  GIB_TRY(mlp_forward(r, pl.fconn2, r.ws + L.cat_conn, L.fconn2, 0, d.B, out + na, pl.apd, nc));  // :273
-  GIB_TRY(mlp_forward(r, pl.fterm2, r.ws + L.g, L.fterm2, 0, d.B, out + na + nc, pl.apd, 1));     // :276
+  {   // modules.py:270-276: the three tier-2 heads
+    MlpJob jobs[3] = {{&pl.fadd2, r.ws + L.cat_add, &L.fadd2, 0, d.B, out, pl.apd, na},
+                      {&pl.fconn2, r.ws + L.cat_conn, &L.fconn2, 0, d.B, out + na, pl.apd, nc},
+                      {&pl.fterm2, r.ws + L.g, &L.fterm2, 0, d.B, out + na + nc, pl.apd, 1}};
+    GIB_TRY(mlp_forward_multi(r, jobs, 3));
+  }
   return 0;
 }
 
@@ -396,11 +524,12 @@ static int readout_backward(const Run& r, const BwdBufs& bb, const float* out, c
     const int ldf = L.fadd1.ld[pl.fadd1.n];
     GIB_TRY(unflatten_dact(T1, ldf, sc + bb.dcat_add, L.fadd2.ld[0], r.ws + L.fadd1.y[pl.fadd1.n], d.N, d.f_add, S,
                            r.st));
-    GIB_TRY(mlp_backward(r, bb, pl.fadd1, hT, L.fadd1, 0, (int)S, T1, dh, Hp, nullptr));
     const int ldc = L.fconn1.ld[pl.fconn1.n];
-    GIB_TRY(unflatten_dact(T1, ldc, sc + bb.dcat_conn, L.fconn2.ld[0], r.ws + L.fconn1.y[pl.fconn1.n], d.N, d.f_conn,
+    GIB_TRY(unflatten_dact(T2, ldc, sc + bb.dcat_conn, L.fconn2.ld[0], r.ws + L.fconn1.y[pl.fconn1.n], d.N, d.f_conn,
                            S, r.st));
-    GIB_TRY(mlp_backward(r, bb, pl.fconn1, hT, L.fconn1, 0, (int)S, T1, dh, Hp, dh));
+    MlpBwdJob jobs[2] = {{&pl.fadd1, hT, &L.fadd1, 0, (int)S, T1, dh, Hp, nullptr},
+                         {&pl.fconn1, hT, &L.fconn1, 0, (int)S, T2, dh, Hp, dh}};
+    GIB_TRY(mlp_backward_multi(r, bb, jobs, 2));
   }
   if (d.model == GIB_MNN) {
     GIB_TRY(bcast_nodes_add(dh, sc + bb.dg, Hp, d.N, S, r.st));
@@ -408,16 +537,19 @@ static int readout_backward(const Run& r, const BwdBufs& bb, const float* out, c
   }
   GIB_TRY(graph_gather_bwd(T1, T2, sc + bb.dg, r.ws + L.attn, r.ws + L.gatt.y[pl.gatt.n], r.ws + L.gemb.y[pl.gemb.n],
                            Gp, d.N, d.B, r.st));
-  GIB_TRY(mlp_backward(r, bb, pl.gemb, hT, L.gemb, 0, (int)S, T2, dh, Hp, dh));
   if (d.model == GIB_EMN) {
     // cat = [h | h]: both halves flow back into h
     const int ldc = L.gatt.ld[0];
-    GIB_TRY(mlp_backward(r, bb, pl.gatt, r.ws + L.cat_att, L.gatt, 0, (int)S, T1, sc + bb.dcat_att, ldc, nullptr));
+    MlpBwdJob jobs[2] = {{&pl.gemb, hT, &L.gemb, 0, (int)S, T2, dh, Hp, dh},
+                         {&pl.gatt, r.ws + L.cat_att, &L.gatt, 0, (int)S, T1, sc + bb.dcat_att, ldc, nullptr}};
+    GIB_TRY(mlp_backward_multi(r, bb, jobs, 2));
     GIB_TRY(sum3_cols(dh, Hp, d.H, sc + bb.dcat_att, ldc, 0, sc + bb.dcat_att, ldc, d.H, dh, Hp, (int)S, r.st));
   } else {
     // only the hidden half of cat(hidden, nodes) needs a gradient: the transposed copy of
     // layer 0 holds just its first H columns (Ct = H), so the output is [S, Hp] directly.
-    GIB_TRY(mlp_backward(r, bb, pl.gatt, r.ws + L.cat_att, L.gatt, 0, (int)S, T1, dh, Hp, dh));
+    MlpBwdJob jobs[2] = {{&pl.gemb, hT, &L.gemb, 0, (int)S, T2, dh, Hp, dh},
+                         {&pl.gatt, r.ws + L.cat_att, &L.gatt, 0, (int)S, T1, dh, Hp, dh}};
+    GIB_TRY(mlp_backward_multi(r, bb, jobs, 2));
   }
   return 0;
 }
@@ -439,9 +571,16 @@ static int node_model_forward(const Run& r, float* out) {
     const float* h = r.ws + L.h[t];
     // mpnn.py:286-288 scales the neighbour state by the bond value for GGNN only
     GIB_TRY(gather_rows(r.ws + L.x0[t], h, Hp, r.ga.ent_src, r.w(), d.model == GIB_GGNN, r.P, r.st));
-    for (int g = 0; g < r.ngroups; ++g) {
-      GIB_TRY(mlp_forward(r, pl.msg[g], r.ws + L.x0[t], L.msg[t], r.tb[g], r.tc[g]));
-      if (d.model == GIB_ATTGGNN) GIB_TRY(mlp_forward(r, pl.att[g], r.ws + L.x0[t], L.att[t], r.tb[g], r.tc[g]));
+    {   // one grouped launch per layer over the bond types (same input rows layout, per-type weights)
+      MlpJob jobs[4];
+      for (int g = 0; g < r.ngroups; ++g)
+        jobs[g] = MlpJob{&pl.msg[g], r.ws + L.x0[t], &L.msg[t], r.tb[g], r.tc[g], nullptr, 0, 0};
+      GIB_TRY(mlp_forward_multi(r, jobs, r.ngroups));
+      if (d.model == GIB_ATTGGNN) {
+        for (int g = 0; g < r.ngroups; ++g)
+          jobs[g] = MlpJob{&pl.att[g], r.ws + L.x0[t], &L.att[t], r.tb[g], r.tc[g], nullptr, 0, 0};
+        GIB_TRY(mlp_forward_multi(r, jobs, r.ngroups));
+      }
     }
     const float* msgs = r.ws + L.msg[t].y[pl.msg[0].n];
     if (d.model == GIB_ATTGGNN)
@@ -509,13 +648,22 @@ static int node_model_backward(const Run& r, const BwdBufs& bb, const float* out
       GIB_TRY(scatter_bwd(T1, sc + bb.dmsum, r.ws + L.msg[t].y[nm], Mp, r.ga.ent_dst, r.w(), pl.msg[0].act, r.P,
                           r.st));
     }
-    for (int g = 0; g < r.ngroups; ++g) {
-      const size_t ro = (size_t)r.tb[g];
-      GIB_TRY(mlp_backward(r, bb, pl.msg[g], r.ws + L.x0[t], L.msg[t], r.tb[g], r.tc[g], T1 + ro * Mp,
-                           dx0 + ro * Hp, Hp, nullptr));
-      if (d.model == GIB_ATTGGNN)
-        GIB_TRY(mlp_backward(r, bb, pl.att[g], r.ws + L.x0[t], L.att[t], r.tb[g], r.tc[g], T2 + ro * Mp,
-                             dx0 + ro * Hp, Hp, dx0 + ro * Hp));
+    {
+      MlpBwdJob jobs[4];
+      for (int g = 0; g < r.ngroups; ++g) {
+        const size_t ro = (size_t)r.tb[g];
+        jobs[g] = MlpBwdJob{&pl.msg[g], r.ws + L.x0[t], &L.msg[t], r.tb[g], r.tc[g], T1 + ro * Mp, dx0 + ro * Hp, Hp,
+                            nullptr};
+      }
+      GIB_TRY(mlp_backward_multi(r, bb, jobs, r.ngroups));
+      if (d.model == GIB_ATTGGNN) {
+        for (int g = 0; g < r.ngroups; ++g) {
+          const size_t ro = (size_t)r.tb[g];
+          jobs[g] = MlpBwdJob{&pl.att[g], r.ws + L.x0[t], &L.att[t], r.tb[g], r.tc[g], T2 + ro * Mp, dx0 + ro * Hp,
+                              Hp, dx0 + ro * Hp};
+        }
+        GIB_TRY(mlp_backward_multi(r, bb, jobs, r.ngroups));
+      }
     }
     // dh[t][src] += (w) dX0   -- deterministic gather-reduce over the by-source CSR
     GIB_TRY(scatter_sum(dh, dx0, Hp, r.ga.src_ptr, r.ga.src_ent, d.model == GIB_GGNN ? r.w() : nullptr, 1, S,
@@ -649,6 +797,18 @@ void make_bwd(const Run& r, BwdBufs& bb) {
   mlp_extent(pl, pl.fadd2, B, big, dw);
   mlp_extent(pl, pl.fconn2, B, big, dw);
   mlp_extent(pl, pl.fterm2, B, big, dw);
+  // grouped backward passes keep one ping/pong slice per member inside GA / GB
+  {
+    size_t types = 64;
+    for (int g = 0; g < r.ngroups && d.model != GIB_EMN; ++g) {
+      size_t w = mlp_max_ld(pl, pl.msg[g]);
+      if (d.model == GIB_ATTGGNN) w = std::max(w, mlp_max_ld(pl, pl.att[g]));
+      types += (size_t)r.tc[g] * w + 32;
+    }
+    big = std::max(big, types);
+    big = std::max(big, S * (mlp_max_ld(pl, pl.fadd1) + mlp_max_ld(pl, pl.fconn1)) + 64);
+    if (d.model != GIB_MNN) big = std::max(big, S * (mlp_max_ld(pl, pl.gatt) + mlp_max_ld(pl, pl.gemb)) + 64);
+  }
   Bump bp;
   bb.GA = bp.take(big); bb.GB = bp.take(big); bb.T1 = bp.take(big); bb.T2 = bp.take(big);
   bb.dw = bp.take(dw);

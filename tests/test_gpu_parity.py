@@ -264,6 +264,32 @@ def test_cpu_tensors_fail_loudly():
         net(fx["nodes"], fx["edges"])
 
 
+def test_attggnn_c3_shape_properties():
+    """BASELINE configs[2] shape (AttentionGGNN hidden=256, 6 passes, 40-atom molecules) on a 192-molecule slice:
+    oracle-checked logits, sub-batch consistency, finite gradients for every parameter."""
+    from graphinvent_b200 import functional as Fn
+    from graphinvent_b200 import synthetic as S
+    from oracle import mpnn_oracle as O
+    C = O.make_constants("AttGGNN", hidden_node_features=256, message_size=256, message_passes=6, max_n_nodes=40,
+                         n_node_features=12, len_f_add_per_node=81)
+    apd = 40 * (81 + 3) + 1
+    sd = O.init_state_dict(C, seed=3)
+    n, e = S.random_graphs(192, 40, 9, 3, seed=1003)
+    nodes, edges = torch.from_numpy(n).float().cuda(), torch.from_numpy(e).float().cuda()
+    target = torch.from_numpy(S.random_targets(192, apd, seed=4)).cuda()
+    net = _build(C, sd)
+    out = net(nodes, edges)
+    Fn.kl_loss(out, target).backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in net.parameters())
+    with torch.no_grad():
+        part = net(nodes[64:128], edges[64:128])
+    assert (out[64:128] - part).abs().max().item() <= 2e-5
+    k = 24
+    ref = O.forward(sd, C, nodes[:k].cpu(), edges[:k].cpu())
+    assert (out[:k].detach().cpu() - ref).abs().max().item() <= LOGIT_TOL
+    assert torch.equal(out[:k].detach().cpu().argmax(1), ref.argmax(1))
+
+
 @pytest.mark.parametrize("cfg", ["C2", "C4_slice"])
 def test_full_size_properties(cfg):
     """BASELINE.json sizes, where the CPU oracle is too slow to be the checker: size-independent
