@@ -1,0 +1,102 @@
+"""
+Batched graph generation with the round post-processing on the device.
+
+Mirror of the reference's `GraphGenerator` (GraphGenerator.py:25-161) for the part that is tensor work:
+`build_graphs()` runs model forward -> softmax/sample -> ONE `gib_generation_round` call per round (decode, validity
+rules, copy-out, apply, reset; the reference issues ~800 ATen ops for the same) until `batch_size` molecules are
+finished; `sample()` returns the finished tensors and likelihood summaries.  Converting tensors to RDKit molecules
+(`graph_to_graph`, GraphGenerator.py:659-804) stays the reference's job -- feed it `generated_nodes/edges/n_nodes`.
+
+The sampler draws with inverse-CDF on `torch.rand` uniforms (same distribution as `Multinomial(1, probs)`, different
+RNG stream); `build_graphs(replay=...)` replays recorded draws instead, which is how the parity tests pin the state
+machine bit-exactly against a trace of the unmodified reference.
+"""
+import ctypes
+
+import torch
+
+from . import functional as Fn
+from ._lib import check, lib
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+class GraphGenerator:
+    def __init__(self, model, batch_size, constants=None, n_atom_types=None, n_formal_charge=None, device="cuda"):
+        C = constants if constants is not None else model.constants
+        self.model, self.batch_size, self.device = model, int(batch_size), torch.device(device)
+        self.N, self.F, self.Ef = C.max_n_nodes, C.n_node_features, C.n_edge_features
+        self.A = n_atom_types if n_atom_types is not None else getattr(C, "n_atom_types")
+        self.CH = n_formal_charge if n_formal_charge is not None else getattr(C, "n_formal_charge")
+        if self.A + self.CH != self.F or self.A * self.CH * self.Ef != C.len_f_add_per_node:
+            raise NotImplementedError("only the 6-tuple action layout (atom type + formal charge node features, no "
+                                      "implicit-H / chirality segment) is supported, as in every shipped configuration")
+        self.apd = self.N * (C.len_f_add_per_node + C.len_f_conn_per_node) + 1
+        self.rounds = 0
+        self._allocate()
+
+    def _allocate(self):
+        B, N, F, Ef, dev = self.batch_size, self.N, self.F, self.Ef, self.device
+        z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=dev)
+        # initialize_graph_batch (GraphGenerator.py:387-423): empty graphs + the dummy graph in slot 0
+        self.nodes, self.edges = z(B, N, F), z(B, N, N, Ef)
+        self.n_nodes = z(B, dt=torch.int32)
+        self.nodes[0] = 1.0
+        self.edges[0, 0, 0, 0] = 1.0
+        self.n_nodes[0] = 1
+        # allocate_graph_tensors (:163-209): finished-graph buffers with one extra batch of slack
+        cap = 2 * B
+        self.capacity = cap
+        self.generated_nodes, self.generated_edges = z(cap, N, F), z(cap, N, N, Ef)
+        self.generated_n_nodes = z(cap, dt=torch.int8)
+        self.likelihoods, self.generated_likelihoods = z(B, 2 * N), z(cap, 2 * N)
+        self.properly_terminated = z(cap, dt=torch.int8)
+        self._counters = z(2, dt=torch.int32)
+        self._scratch = torch.empty(lib.gib_generation_scratch_bytes(B), dtype=torch.uint8, device=dev)
+
+    @torch.no_grad()
+    def build_graphs(self, replay=None, generator=None):
+        """replay: optional iterable of (action int32 [B], likelihood float32 [B]) per round (the model is then not
+        evaluated); returns the number of finished molecules (may exceed batch_size, as in the reference)."""
+        B = self.batch_size
+        n_generated, rnd = 0, 0
+        replay = iter(replay) if replay is not None else None
+        st = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        while n_generated < B:
+            if rnd >= 2 * self.N:
+                raise RuntimeError("generation needs more than 2*max_n_nodes rounds: the per-slot likelihood buffer "
+                                   "(GraphGenerator.py:173, 'the 2 is arbitrary') would overflow, as in the reference")
+            if replay is not None:
+                try:
+                    action, lik = next(replay)
+                except StopIteration:
+                    raise RuntimeError("replay trace ended before batch_size molecules were finished") from None
+                action = action.to(self.device, torch.int32).contiguous()
+                lik = lik.to(self.device, torch.float32).contiguous()
+            else:
+                out = self.model(self.nodes, self.edges)          # GraphGenerator.py:121
+                action, lik = Fn.sample_actions(out, generator=generator)
+            check(lib.gib_generation_round(B, self.N, self.F, self.Ef, self.A, self.CH, rnd, _ptr(action), _ptr(lik),
+                                           _ptr(self.nodes), _ptr(self.edges), _ptr(self.n_nodes),
+                                           _ptr(self.likelihoods), _ptr(self.generated_nodes),
+                                           _ptr(self.generated_edges), _ptr(self.generated_n_nodes),
+                                           _ptr(self.generated_likelihoods), _ptr(self.properly_terminated),
+                                           self.capacity, _ptr(self._counters), _ptr(self._scratch), st),
+                  "gib_generation_round")
+            n_generated = int(self._counters[0].item())           # the loop condition lives on the host (:118)
+            rnd += 1
+        self.rounds = rnd
+        return n_generated
+
+    def sample(self, generator=None):
+        """returns (generated_nodes, generated_edges, generated_n_nodes) of the first batch_size finished molecules,
+        the non-zero per-action likelihoods, log(sum of likelihoods) per molecule and the properly-terminated flags
+        (GraphGenerator.sample :48-96 without the RDKit conversion)."""
+        self.build_graphs(generator=generator)
+        B = self.batch_size
+        final = torch.log(self.generated_likelihoods.sum(dim=1)[:B])              # :81-83
+        flat = self.generated_likelihoods[self.generated_likelihoods != 0]        # :86-88
+        graphs = (self.generated_nodes[:B], self.generated_edges[:B], self.generated_n_nodes[:B])
+        return graphs, flat, final, self.properly_terminated[:B]

@@ -142,6 +142,20 @@ int gib_graph_gather(float* g, float* att, const float* en, const float* em, int
 int gib_sample_actions(const float* out, int B, int apd, const float* uniforms, int* action,
                        float* likelihood, gib_stream stream);
 
+/* ---- one round of batched graph generation on the device: decode the sampled flat APD
+ *      index per slot, validity rules, copy terminated graphs out (pre-action state; terminate-sampled first, then
+ *      invalid, ascending), apply add / connect, reset, re-stamp the dummy graph in slot 0.  Replaces
+ *      GraphGenerator.get_actions / get_invalid_actions / copy_terminated_graphs / apply_actions / reset_graphs
+ *      (GraphGenerator.py:467-657, 340-385, 211-338, 425-465).  6-tuple action layout (no implicit-H / chirality).
+ *      State: nodes [B,N,F] f32, edges [B,N,N,Ef] f32, n_nodes [B] i32, likelihoods [B,2N] f32; outputs
+ *      gen_* with `capacity` rows; counters[0] = n_generated (in/out), counters[1] = graphs written this round. ---- */
+size_t gib_generation_scratch_bytes(int B);
+int gib_generation_round(int B, int N, int F, int Ef, int n_atom_types, int n_charges, int round,
+                         const int* action, const float* likelihood, float* nodes, float* edges, int* n_nodes,
+                         float* likelihoods, float* gen_nodes, float* gen_edges, signed char* gen_n_nodes,
+                         float* gen_likelihoods, signed char* properly_terminated, int capacity, int* counters,
+                         void* scratch, gib_stream stream);
+
 /* ---- measurement hooks: CUDA-event timing per kernel class on the launching stream.
  *      class 0 = forward/dX GEMMs, 1 = dW GEMMs (+ split-K reduce), 2 = scatter-aggregate (K2).
  *      work = algorithmic FLOPs (classes 0,1) or bytes (class 2).  Collect after a stream sync. -- */
