@@ -510,10 +510,18 @@ static int readout_backward(const Run& r, const BwdBufs& bb, const float* out, c
   Head heads[3] = {{&pl.fadd2, &L.fadd2, r.ws + L.cat_add, 0, na, bb.dcat_add, L.fadd2.ld[0]},
                    {&pl.fconn2, &L.fconn2, r.ws + L.cat_conn, na, nc, bb.dcat_conn, L.fconn2.ld[0]},
                    {&pl.fterm2, &L.fterm2, r.ws + L.g, na + nc, 1, bb.dgterm, Gp}};
-  for (const Head& h : heads) {
-    const Lin& last = pl.lins[h.m->first + h.m->n - 1];
-    GIB_TRY(dact_slice(T1, last.Rp, dout, out, pl.apd, h.off, h.width, ACT_SELU, d.B, r.st));
-    GIB_TRY(mlp_backward(r, bb, *h.m, h.x0, *h.a, 0, d.B, T1, sc + h.dcat, h.ldcat, nullptr));
+  {   // three heads of equal depth: top gradients into three slices of T1, then one grouped backward
+    MlpBwdJob jobs[3];
+    size_t off = 0;
+    for (int i = 0; i < 3; ++i) {
+      const Head& h = heads[i];
+      const Lin& last = pl.lins[h.m->first + h.m->n - 1];
+      float* gt = T1 + off;
+      GIB_TRY(dact_slice(gt, last.Rp, dout, out, pl.apd, h.off, h.width, ACT_SELU, d.B, r.st));
+      jobs[i] = MlpBwdJob{h.m, h.x0, h.a, 0, d.B, gt, sc + h.dcat, h.ldcat, nullptr};
+      off += ((size_t)d.B * last.Rp + 31) & ~(size_t)31;
+    }
+    GIB_TRY(mlp_backward_multi(r, bb, jobs, 3));
   }
   // d(graph embedding) = tail columns of the two cat gradients + the terminate head
   GIB_TRY(sum3_cols(sc + bb.dg, Gp, pl.G, sc + bb.dcat_add, L.fadd2.ld[0], na, sc + bb.dcat_conn, L.fconn2.ld[0], nc,
@@ -588,14 +596,19 @@ static int node_model_forward(const Run& r, float* out) {
                               r.w(), S, r.st));
     else
       GIB_TRY(scatter_sum(r.ws + L.msum[t], msgs, Mp, r.ga.dst_ptr, r.ga.dst_ent, r.w(), 0, S, r.st));
-    GemmNT p;
-    p.A = r.ws + L.msum[t]; p.lda = Mp; p.B = r.packed + ih.ow; p.ldb = ih.Cp; p.C = r.ws + L.gi[t]; p.ldc = ih.Rp;
-    p.M = (int)S; p.N = ih.Rp; p.K = ih.Cp; p.bias = r.packed + ih.ob; p.act = ACT_NONE; p.mode = EPI_ACT;
-    p.n_store = p.n_valid = ih.Rp;
-    GIB_TRY(gemm_nt(p, r.st));
-    p.A = h; p.lda = Hp; p.B = r.packed + hh.ow; p.ldb = hh.Cp; p.C = r.ws + L.gh[t]; p.ldc = hh.Rp;
-    p.N = hh.Rp; p.K = hh.Cp; p.bias = r.packed + hh.ob; p.n_store = p.n_valid = hh.Rp;
-    GIB_TRY(gemm_nt(p, r.st));
+    {   // the two GRU input projections are independent: one grouped launch
+      GemmNT ps[2];
+      GemmNT& p = ps[0];
+      p.A = r.ws + L.msum[t]; p.lda = Mp; p.B = r.packed + ih.ow; p.ldb = ih.Cp; p.C = r.ws + L.gi[t]; p.ldc = ih.Rp;
+      p.M = (int)S; p.N = ih.Rp; p.K = ih.Cp; p.bias = r.packed + ih.ob; p.act = ACT_NONE; p.mode = EPI_ACT;
+      p.n_store = p.n_valid = ih.Rp; p.work = 2.0 * S * (double)ih.R * ih.C;
+      GemmNT& q2 = ps[1];
+      q2 = p;
+      q2.A = h; q2.lda = Hp; q2.B = r.packed + hh.ow; q2.ldb = hh.Cp; q2.C = r.ws + L.gh[t]; q2.ldc = hh.Rp;
+      q2.N = hh.Rp; q2.K = hh.Cp; q2.bias = r.packed + hh.ob; q2.n_store = q2.n_valid = hh.Rp;
+      q2.work = 2.0 * S * (double)hh.R * hh.C;
+      GIB_TRY(gemm_nt_group(ps, 2, r.st));
+    }
     GIB_TRY(gru_fwd(r.ws + L.h[t + 1], r.ws + L.gi[t], r.ws + L.gh[t], h, Hp, r.ga.dst_ptr, S, r.st));
   }
   return readout_forward(r, out);
@@ -626,14 +639,18 @@ static int node_model_backward(const Run& r, const BwdBufs& bb, const float* out
     q.dW = r.grads[hh.pw]; q.dbias = r.grads[hh.pb]; q.R = hh.R; q.C = hh.C; q.Rb = hh.Rb; q.Rbp = hh.Rbp;
     q.rs = hh.rs; q.cs = hh.cs;
     GIB_TRY(gemm_dw(q, r.st));
-    GemmNT p;  // dMsum = dgi W_ih
-    p.A = sc + bb.dgi; p.lda = ih.Rp; p.B = r.packed + ih.owt; p.ldb = ih.Rp; p.C = sc + bb.dmsum; p.ldc = Mp;
-    p.M = (int)S; p.N = ih.Ctp; p.K = ih.Rp; p.mode = EPI_ACT; p.act = ACT_NONE; p.n_store = p.n_valid = ih.Ctp;
-    GIB_TRY(gemm_nt(p, r.st));
-    // dh[t] = dgh W_hh + direct   (written over dh: dh[t+1] is dead after gru_bwd)
-    p.A = sc + bb.dgh; p.lda = hh.Rp; p.B = r.packed + hh.owt; p.ldb = hh.Rp; p.C = dh; p.ldc = Hp;
-    p.N = hh.Ctp; p.K = hh.Rp; p.mode = EPI_ADD; p.aux = dh_dir; p.ldaux = Hp; p.n_store = p.n_valid = hh.Ctp;
-    GIB_TRY(gemm_nt(p, r.st));
+    {   // dMsum = dgi W_ih  and  dh[t] = dgh W_hh + direct  (dh[t+1] is dead after gru_bwd): one grouped launch
+      GemmNT ps[2];
+      GemmNT& p = ps[0];
+      p.A = sc + bb.dgi; p.lda = ih.Rp; p.B = r.packed + ih.owt; p.ldb = ih.Rp; p.C = sc + bb.dmsum; p.ldc = Mp;
+      p.M = (int)S; p.N = ih.Ctp; p.K = ih.Rp; p.mode = EPI_ACT; p.act = ACT_NONE; p.n_store = p.n_valid = ih.Ctp;
+      p.work = 2.0 * S * (double)ih.R * ih.C;
+      GemmNT& q2 = ps[1];
+      q2.A = sc + bb.dgh; q2.lda = hh.Rp; q2.B = r.packed + hh.owt; q2.ldb = hh.Rp; q2.C = dh; q2.ldc = Hp;
+      q2.M = (int)S; q2.N = hh.Ctp; q2.K = hh.Rp; q2.mode = EPI_ADD; q2.aux = dh_dir; q2.ldaux = Hp;
+      q2.n_store = q2.n_valid = hh.Ctp; q2.work = 2.0 * S * (double)hh.R * hh.C;
+      GIB_TRY(gemm_nt_group(ps, 2, r.st));
+    }
     // through the aggregation into the per-bond message MLPs
     float* T1 = sc + bb.T1;
     float* T2 = sc + bb.T2;
@@ -807,6 +824,7 @@ void make_bwd(const Run& r, BwdBufs& bb) {
     }
     big = std::max(big, types);
     big = std::max(big, S * (mlp_max_ld(pl, pl.fadd1) + mlp_max_ld(pl, pl.fconn1)) + 64);
+    big = std::max(big, B * (mlp_max_ld(pl, pl.fadd2) + mlp_max_ld(pl, pl.fconn2) + mlp_max_ld(pl, pl.fterm2)) + 128);
     if (d.model != GIB_MNN) big = std::max(big, S * (mlp_max_ld(pl, pl.gatt) + mlp_max_ld(pl, pl.gemb)) + 64);
   }
   Bump bp;
