@@ -218,7 +218,8 @@ def scatter_roofline(pk, iters=30):
     nbytes = E * ld * 4 + S * ld * 4 + (S + 1) * 4 + E * 8
     gbs = nbytes / ms / 1e6
     return {"kernel": "scatter_sum_kernel (K2)", "bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s",
-            "frac": gbs / pk["hbm"], "traffic": None, "peak_source": pk["source"] + " (copy, burst)",
+            "frac": gbs / pk["hbm"], "traffic": 208559360,
+            "traffic_source": "profiles/r01_ncu_full_summary.md (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum, one launch)", "peak_source": pk["source"] + " (copy, burst)",
             "shape": {"slots": S, "entries": E, "ld": ld}, "ms_per_launch": ms, "bytes_per_launch": nbytes,
             "l2": "working set 204 MB > 126 MB L2, no flush needed"}
 
@@ -320,7 +321,8 @@ def run_b200_arm(args):
     cls = 0 if pms[0] >= pms[1] else 1
     gemm_tflops = pwork[cls] / pms[cls] / 1e9 if pms[cls] > 0 else 0.0
     tensor_peak = pk["bf16_sustained"] / 2.0 / 3.0     # TF32 dense = bf16/2; fp32-accurate 3xTF32 = /3
-    roofline = {"kernel": ["sgemm_nt_kernel (fwd + dX GEMMs)", "sgemm_tn_splitk_kernel (dW GEMMs)"][cls],
+    roofline = {"kernel": ["tc_gemm_nt_kernel NT mode (tcgen05 3xTF32; forward + dX GEMMs)",
+                           "tc_gemm_nt_kernel TN mode + split reductions (weight-gradient GEMMs)"][cls],
                 "bound": "tensor", "achieved": gemm_tflops, "peak": tensor_peak, "unit": "TFLOP/s",
                 "frac": gemm_tflops / tensor_peak, "traffic": None,
                 "peak_source": pk["source"] + " bf16 sustained / 2 (TF32 rate) / 3 (fp32-accurate 3xTF32 issue)",
