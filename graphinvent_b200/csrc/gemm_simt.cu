@@ -15,7 +15,7 @@
 namespace gib {
 
 constexpr int BK = 16;
-constexpr int kColsumSplits = 64;   // row chunks of the two-stage bias-gradient column sum
+constexpr int kColsumSplits = 148;  // row chunks (one block each) of the two-stage bias-gradient column sum
 
 // ------------------------------------------------------------------------------------
 // C[M,N] = epilogue( A[M,K] * B[N,K]^T )       (both operands K-contiguous)
@@ -384,23 +384,36 @@ static int launch_reduce(const float* ws, int splits, const GemmDW& q, const flo
   return 0;
 }
 
-// part[z][n] = sum over the z-th row chunk of G[m, n]  (fixed order inside the chunk; chunks reduced in order)
+// part[z][n] = sum over the z-th row chunk of G[m, n]  (fixed order inside the chunk; chunks reduced in order).
+// One block per row chunk, whole rows read with float4 (fully coalesced); thread t owns float4 column t % (Nn/4) and
+// every (256 / (Nn/4))-th row of the chunk, partial sums meet in shared memory in a fixed order.
 __global__ void __launch_bounds__(256) colsum_partial_kernel(float* __restrict__ part, const float* __restrict__ G,
                                                              int ldg, int M, int Nn) {
-  __shared__ float sm[8][33];
-  const int n = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int wy = threadIdx.x >> 5;
-  const int rows = ceil_div(M, (int)gridDim.y);
-  const int m0 = blockIdx.y * rows, m1 = min(M, m0 + rows);
-  float s = 0.f;
-  if (n < Nn)
-    for (int m = m0 + wy; m < m1; m += 8) s += G[(size_t)m * ldg + n];
-  sm[wy][threadIdx.x & 31] = s;
-  __syncthreads();
-  if (wy == 0 && n < Nn) {
-    float t = 0.f;
-    for (int k = 0; k < 8; ++k) t += sm[k][threadIdx.x];
-    part[(size_t)blockIdx.y * Nn + n] = t;
+  __shared__ float4 sm[256];
+  const int n4 = Nn >> 2;                       // float4 columns per row (Nn is a multiple of 16)
+  const int rows = ceil_div(M, (int)gridDim.x);
+  const int m0 = blockIdx.x * rows, m1 = min(M, m0 + rows);
+  for (int c0 = 0; c0 < n4; c0 += 256) {        // Nn <= 1024 handled in one sweep per 256 float4 columns
+    const int width = min(256, n4 - c0);        // active float4 columns in this sweep
+    const int lanes = 256 / width;              // row lanes sharing the sweep
+    const int col = threadIdx.x % width, rl = threadIdx.x / width;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (rl < lanes)
+      for (int m = m0 + rl; m < m1; m += lanes) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(G + (size_t)m * ldg) + c0 + col);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    if (rl == 0) {
+      float4 t = sm[col];
+      for (int k = 1; k < lanes; ++k) {
+        const float4 u = sm[k * width + col];
+        t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+      }
+      reinterpret_cast<float4*>(part + (size_t)blockIdx.x * Nn)[c0 + col] = t;
+    }
+    __syncthreads();
   }
 }
 
@@ -440,7 +453,7 @@ int gemm_dw(const GemmDW& q, cudaStream_t st) {
     GIB_TRY(gemm_dw_tc_partials(q, &tsplits, st));
     float* part = q.scratch + (size_t)tsplits * q.Nn * q.Kk;       // [kColsumSplits][Nn] partial column sums
     if (q.dbias) {
-      colsum_partial_kernel<<<dim3(ceil_div(q.Nn, 32), kColsumSplits), 256, 0, st>>>(part, q.G, q.ldg, q.M, q.Nn);
+      colsum_partial_kernel<<<kColsumSplits, 256, 0, st>>>(part, q.G, q.ldg, q.M, q.Nn);
       GIB_LAUNCH_CHECK();
     }
     return launch_reduce(q.scratch, tsplits, q, part, kColsumSplits, st);
