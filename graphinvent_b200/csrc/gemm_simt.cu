@@ -15,7 +15,7 @@
 namespace gib {
 
 constexpr int BK = 16;
-constexpr int kColsumSplits = 148;  // row chunks (one block each) of the two-stage bias-gradient column sum
+constexpr int kColsumSplits = 296;  // row chunks (one block each) of the two-stage bias-gradient column sum
 
 // ------------------------------------------------------------------------------------
 // C[M,N] = epilogue( A[M,K] * B[N,K]^T )       (both operands K-contiguous)
@@ -398,11 +398,21 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(float* __restrict__
     const int lanes = 256 / width;              // row lanes sharing the sweep
     const int col = threadIdx.x % width, rl = threadIdx.x / width;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (rl < lanes)
-      for (int m = m0 + rl; m < m1; m += lanes) {
+    if (rl < lanes) {
+      int m = m0 + rl;
+      for (; m + 3 * lanes < m1; m += 4 * lanes) {      // four row loads in flight, summed in ascending row order
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          v[u] = __ldg(reinterpret_cast<const float4*>(G + (size_t)(m + u * lanes) * ldg) + c0 + col);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+      }
+      for (; m < m1; m += lanes) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(G + (size_t)m * ldg) + c0 + col);
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
       }
+    }
     sm[threadIdx.x] = acc;
     __syncthreads();
     if (rl == 0) {
