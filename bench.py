@@ -167,7 +167,7 @@ def cpu_train_steps(cfg, steps, warmup, budget_s=None, seed=1002):
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
-        return 0            # under torchrun only rank 0 measures the CPU path
+        return None         # under torchrun only rank 0 measures the CPU path
     B, times, loss = cpu_train_steps(args.config, args.steps, args.warmup)
     total = sum(times)
     value = B * len(times) / total
@@ -182,8 +182,7 @@ def run_reference_arm(args):
                              "sample": f"{len(times)} full steps of batch {B}", "os_cpu_count": os.cpu_count()},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "final_loss": loss}
-    print(json.dumps(line), flush=True)
-    return 0
+    return line
 
 
 # ------------------------------------------------------------------------------------------
@@ -312,7 +311,7 @@ def run_b200_arm(args):
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
-        return 0
+        return None
 
     pk = peaks()
     value = world * B * args.steps / (ms_total / 1e3)
@@ -353,10 +352,25 @@ def run_b200_arm(args):
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                                 "sample": f"{len(times)} full steps of batch {Bc} after 1 warm-up (oracle port, "
                                           "fwd+kl_loss+bwd+adam)", "os_cpu_count": os.cpu_count()}
-    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
-    return 0
+    return line
+
+
+class _StdoutToStderr:
+    """NCCL (and anything else native) may print to fd 1 (e.g. "NCCL version ..."): the contract is ONE JSON line on
+    stdout, so fd 1 is pointed at stderr while the benchmark runs and restored just before the line is printed."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
 
 
 def main():
@@ -371,10 +385,16 @@ def main():
     if args.impl == "reference":
         args.steps = args.steps if args.steps is not None else 5
         args.warmup = args.warmup if args.warmup is not None else 1
-        return run_reference_arm(args)
-    args.steps = args.steps if args.steps is not None else 30
-    args.warmup = args.warmup if args.warmup is not None else 5
-    return run_b200_arm(args)
+        with _StdoutToStderr():
+            line = run_reference_arm(args)
+    else:
+        args.steps = args.steps if args.steps is not None else 30
+        args.warmup = args.warmup if args.warmup is not None else 5
+        with _StdoutToStderr():
+            line = run_b200_arm(args)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+    return 0
 
 
 if __name__ == "__main__":
