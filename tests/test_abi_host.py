@@ -138,3 +138,17 @@ def test_synthetic_generator_matches_survey_statistics():
         assert (nodes.sum(-1) == 2).all()                              # atom type + neutral charge
     t = S.random_targets(8, 625, seed=0)
     assert np.allclose(t.sum(1), 1, atol=1e-5) and (t > 0).all()
+
+
+def test_raw_hdf5_reader_matches_the_golden_rows():
+    import os
+    from graphinvent_b200 import data
+    path = "/root/reference/data/pre-training/gdb13_1K/train.h5"
+    if not os.path.exists(path):
+        pytest.skip("/root/reference not mounted")
+    nodes, edges, apds = data.read_hdf5_raw(path, 13, 8, 3, 625)
+    z = np.load(os.path.join(ROOT, "tests", "golden", "gdb13_rows.npz"))
+    assert nodes.shape == (12000, 13, 8) and edges.shape == (12000, 13, 13, 3) and apds.shape == (12000, 625)
+    assert (nodes[:256] == z["nodes"]).all() and (edges[:256] == z["edges"]).all() and (apds[:256] == z["apds"]).all()
+    with pytest.raises(ValueError):
+        data.read_hdf5_raw(path, 13, 8, 3, 624)

@@ -256,6 +256,16 @@ def test_module_protocol_eval_nograd_deepcopy_statedict_reentrancy():
     assert (net(nodes[:3], edges[:3]) - o3[:3]).abs().max().item() <= 2e-5
 
 
+def test_int8_inputs_are_widened_on_the_device():
+    """§8f rank 3: int8 batches (the reference's on-disk dtype) go to the device as 1 byte per element"""
+    fx = load_small("GGNN")
+    net = _build(fx["C"], fx["sd"])
+    with torch.no_grad():
+        a = net(fx["nodes"].cuda(), fx["edges"].cuda())
+        b = net(fx["nodes"].to(torch.int8).cuda(), fx["edges"].to(torch.int8).cuda())
+    assert torch.equal(a, b)
+
+
 def test_cpu_tensors_fail_loudly():
     fx = load_small("GGNN")
     from graphinvent_b200.gnn import mpnn
