@@ -56,12 +56,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// bounded wait: ~1 s of wall clock, then trap (surfaces as a CUDA error instead of hanging the box)
+// bounded wait: ~10 s of wall clock, then trap (surfaces as a CUDA error instead of hanging the box)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity))
-    if (clock64() - t0 > 2000000000LL) __trap();
+    if (clock64() - t0 > 20000000000LL) __trap();   // ~10 s: a dead-lock, not contention
 }
 
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
