@@ -243,7 +243,10 @@ int gib_linear_bwd_dw(const float* G, int ldg, int Nn, const float* X, int ldx, 
   GemmDW q;
   q.G = G; q.ldg = ldg; q.Nn = Nn; q.X = X; q.ldx = ldx; q.Kk = Kk; q.M = M; q.dW = dW; q.dbias = dbias;
   q.R = R; q.C = C; q.Rb = R; q.Rbp = Nn; q.rs = C; q.cs = 1; q.scratch = reinterpret_cast<float*>(scratch);
-  return gemm_dw(q, ST(stream));
+  q.half_floats = gemm_dw_half_floats(M, Nn, Kk);
+  const int rc = gemm_dw(q, ST(stream));
+  const int rj = dw_join(ST(stream));
+  return rc ? rc : rj;
 }
 int gib_scatter_sum(float* out, const float* msg, int ld, const int* ptr, const int* ent, const float* w, long long S,
                     gib_stream stream) {

@@ -45,7 +45,8 @@ struct GemmDW {
   float* dW = nullptr; float* dbias = nullptr;        // either may be null
   int R = 0, C = 0, Rb = 0, Rbp = 0;
   long long rs = 0, cs = 1;
-  float* scratch = nullptr;                           // >= gemm_dw_scratch_floats(M, Nn, Kk)
+  float* scratch = nullptr;                           // >= gemm_dw_scratch_floats(...) of the largest call: two halves
+  size_t half_floats = 0;                             // size of one half (same value for every call on this scratch)
   double work = 0;                                    // algorithmic FLOPs (0: derive)
 };
 
@@ -62,6 +63,8 @@ void gemm_dw_plan(int M, int Nn, int Kk, int* splits, int* chunk);
 void tc_dw_plan(int M, int Nn, int Kk, int* splits, int* chunk);
 bool tc_dw_eligible(const GemmDW& q);
 int gemm_dw_tc_partials(const GemmDW& q, int* splits_out, cudaStream_t st);
-size_t gemm_dw_scratch_floats(int M, int Nn, int Kk);
+size_t gemm_dw_scratch_floats(int M, int Nn, int Kk);   // both halves
+size_t gemm_dw_half_floats(int M, int Nn, int Kk);
+int dw_join(cudaStream_t st);                            // drain the helper side stream into `st`
 
 }  // namespace gib

@@ -427,12 +427,51 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(float* __restrict__
   }
 }
 
-size_t gemm_dw_scratch_floats(int M, int Nn, int Kk) {
+// ---- helper side stream ------------------------------------------------------------------------------------
+// The tensor-core GEMM CTAs leave ~8K registers and ~14 KB of shared memory free on every SM, exactly one 256-thread
+// block of the two reduction helpers (32 registers each).  They therefore run on a library-owned side stream,
+// concurrently with the NEXT tensor-core launches of the main stream, instead of serialising ~12 us per layer.
+//   job i (scratch half i&1):  main: [wait done(i-2)] TN partials -> record tn(i)
+//                              side: wait tn(i); column sums of G; fixed-order reduction into the gradients; record done(i)
+//                              main: ... dX GEMM of the layer, TN of the next layer (job i+1), then wait done(i)
+// so at most one job is pending, and it is complete before anything can overwrite the buffers it reads (the G
+// operand's ping/pong partner is only rewritten by the dX GEMM that follows job i+1).  dw_join() drains the side
+// stream into the caller's stream; every C-ABI entry that uses gemm_dw calls it before returning.
+static cudaStream_t g_side = nullptr;
+static cudaEvent_t g_ev_tn[2], g_ev_done[2];
+static bool g_done_valid[2] = {false, false};
+static long long g_dw_calls = 0;
+static int g_pending = -1;        // scratch half of the job whose completion the main stream has not waited for yet
+
+static int dw_side_init() {
+  if (g_side) return 0;
+  GIB_CUDA_TRY(cudaStreamCreateWithFlags(&g_side, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    GIB_CUDA_TRY(cudaEventCreateWithFlags(&g_ev_tn[i], cudaEventDisableTiming));
+    GIB_CUDA_TRY(cudaEventCreateWithFlags(&g_ev_done[i], cudaEventDisableTiming));
+  }
+  return 0;
+}
+
+int dw_join(cudaStream_t st) {
+  if (g_pending >= 0) {
+    GIB_CUDA_TRY(cudaStreamWaitEvent(st, g_ev_done[g_pending], 0));
+    g_pending = -1;
+  }
+  return 0;
+}
+
+size_t gemm_dw_half_floats(int M, int Nn, int Kk) {
   int splits, chunk, s2, c2;
   gemm_dw_plan(M, Nn, Kk, &splits, &chunk);
   tc_dw_plan(M, Nn, Kk, &s2, &c2);       // the tensor-core path may pick a different split count
   if (s2 > splits) splits = s2;
-  return (size_t)splits * Nn * Kk + (size_t)(splits > kColsumSplits ? splits : kColsumSplits) * Nn;
+  return (((size_t)splits * Nn * Kk + (size_t)(splits > kColsumSplits ? splits : kColsumSplits) * Nn) + 63) & ~(size_t)63;
+}
+
+size_t gemm_dw_scratch_floats(int M, int Nn, int Kk) {
+  // two halves: the side stream may still be reducing job i while job i+1 writes its partials
+  return 2 * gemm_dw_half_floats(M, Nn, Kk);
 }
 
 void gemm_dw_plan(int M, int Nn, int Kk, int* splits, int* chunk) {
@@ -456,25 +495,40 @@ int gemm_dw(const GemmDW& q, cudaStream_t st) {
     return -2;
   }
   ProfScope prof(PROF_GEMM_DW, q.work > 0 ? q.work : 2.0 * q.M * (double)q.R * q.C, st);
+  GIB_TRY(dw_side_init());
+  const int half = (int)(g_dw_calls++ & 1);
+  float* const scratch = q.scratch + (size_t)half * q.half_floats;
+  if (g_done_valid[half]) GIB_CUDA_TRY(cudaStreamWaitEvent(st, g_ev_done[half], 0));   // job i-2 released this half
   if (g_use_tc && q.dW && tc_dw_eligible(q)) {
-    // tensor-core partials (tcgen05, MN-major operands straight from the row-major activations), then the same
-    // fixed-order split reduction; the bias gradient is a separate column sum of G
+    // tensor-core partials (tcgen05, MN-major operands straight from the row-major activations) on the main stream;
+    // bias column sums + the fixed-order split reduction on the side stream
     int tsplits = 0;
-    GIB_TRY(gemm_dw_tc_partials(q, &tsplits, st));
-    float* part = q.scratch + (size_t)tsplits * q.Nn * q.Kk;       // [kColsumSplits][Nn] partial column sums
+    GemmDW q2 = q;
+    q2.scratch = scratch;
+    GIB_TRY(gemm_dw_tc_partials(q2, &tsplits, st));
+    GIB_CUDA_TRY(cudaEventRecord(g_ev_tn[half], st));
+    GIB_CUDA_TRY(cudaStreamWaitEvent(g_side, g_ev_tn[half], 0));
+    float* part = scratch + (size_t)tsplits * q.Nn * q.Kk;         // [kColsumSplits][Nn] partial column sums
     if (q.dbias) {
-      colsum_partial_kernel<<<kColsumSplits, 256, 0, st>>>(part, q.G, q.ldg, q.M, q.Nn);
+      colsum_partial_kernel<<<kColsumSplits, 256, 0, g_side>>>(part, q.G, q.ldg, q.M, q.Nn);
       GIB_LAUNCH_CHECK();
     }
-    return launch_reduce(q.scratch, tsplits, q, part, kColsumSplits, st);
+    GIB_TRY(launch_reduce(scratch, tsplits, q, part, kColsumSplits, g_side));
+    GIB_CUDA_TRY(cudaEventRecord(g_ev_done[half], g_side));
+    g_done_valid[half] = true;
+    const int prev = g_pending;       // the job before this one must be complete before the caller's next dX GEMM
+    g_pending = half;
+    if (prev >= 0 && prev != half) GIB_CUDA_TRY(cudaStreamWaitEvent(st, g_ev_done[prev], 0));
+    return 0;
   }
+  GIB_TRY(dw_join(st));               // fp32 SIMT path: everything on the caller's stream, nothing left pending
   int splits, chunk;
   gemm_dw_plan(q.M, q.Nn, q.Kk, &splits, &chunk);
   GemmTN p;
   p.G = q.G; p.ldg = q.ldg; p.X = q.X; p.ldx = q.ldx; p.M = q.M; p.Nn = q.Nn; p.Kk = q.Kk;
   p.chunk_rows = chunk;
-  p.ws = q.scratch;
-  p.ws_bias = q.dbias ? q.scratch + (size_t)splits * q.Nn * q.Kk : nullptr;
+  p.ws = scratch;
+  p.ws_bias = q.dbias ? scratch + (size_t)splits * q.Nn * q.Kk : nullptr;
   if (q.dW) {
     dim3 grid(ceil_div(q.Kk, 128), ceil_div(q.Nn, 128), splits);
     sgemm_tn_splitk_kernel<128, 128, 2, 2><<<grid, 256, 0, st>>>(p);

@@ -305,7 +305,7 @@ static int mlp_backward(const Run& r, const BwdBufs& bb, const Mlp& m, const flo
     q.dW = r.grads[L.pw] + L.src_off;
     q.dbias = L.pb >= 0 ? r.grads[L.pb] : nullptr;
     q.R = L.R; q.C = L.C; q.Rb = L.Rb; q.Rbp = L.Rbp; q.rs = L.rs; q.cs = L.cs;
-    q.scratch = r.scratch + bb.dw;
+    q.scratch = r.scratch + bb.dw; q.half_floats = bb.dw_half;
     q.work = 2.0 * rows * (double)L.R * L.C;
     GIB_TRY(gemm_dw(q, r.st));
     if (l > 1 || dX0) {
@@ -328,6 +328,8 @@ static int mlp_backward(const Run& r, const BwdBufs& bb, const Mlp& m, const flo
       G = p.C;
     }
   }
+  // single-layer MLP: the pending side-stream job reads the caller's Gtop buffer -- finish it before returning
+  if (m.n == 1) GIB_TRY(dw_join(r.st));
   return 0;
 }
 
@@ -419,7 +421,7 @@ static int mlp_backward_multi(const Run& r, const BwdBufs& bb, const MlpBwdJob* 
       q.dW = r.grads[L.pw] + L.src_off;
       q.dbias = L.pb >= 0 ? r.grads[L.pb] : nullptr;
       q.R = L.R; q.C = L.C; q.Rb = L.Rb; q.Rbp = L.Rbp; q.rs = L.rs; q.cs = L.cs;
-      q.scratch = r.scratch + bb.dw;
+      q.scratch = r.scratch + bb.dw; q.half_floats = bb.dw_half;
       q.work = 2.0 * j.rows * (double)L.R * L.C;
       GIB_TRY(gemm_dw(q, r.st));
       if (l > 1) {
@@ -447,6 +449,7 @@ static int mlp_backward_multi(const Run& r, const BwdBufs& bb, const MlpBwdJob* 
       for (int k = 0; k < np; ++k) G[idx[k]] = ps[k].C;
     }
   }
+  if (jobs[0].m->n == 1) GIB_TRY(dw_join(r.st));   // see mlp_backward
   return 0;
 }
 
@@ -633,7 +636,7 @@ static int node_model_backward(const Run& r, const BwdBufs& bb, const float* out
     GemmDW q;
     q.G = sc + bb.dgi; q.ldg = ih.Rp; q.Nn = ih.Rp; q.X = r.ws + L.msum[t]; q.ldx = Mp; q.Kk = ih.Cp; q.M = (int)S;
     q.dW = r.grads[ih.pw]; q.dbias = r.grads[ih.pb]; q.R = ih.R; q.C = ih.C; q.Rb = ih.Rb; q.Rbp = ih.Rbp;
-    q.rs = ih.rs; q.cs = ih.cs; q.scratch = sc + bb.dw;
+    q.rs = ih.rs; q.cs = ih.cs; q.scratch = sc + bb.dw; q.half_floats = bb.dw_half;
     GIB_TRY(gemm_dw(q, r.st));
     q.G = sc + bb.dgh; q.ldg = hh.Rp; q.Nn = hh.Rp; q.X = h; q.ldx = Hp; q.Kk = hh.Cp;
     q.dW = r.grads[hh.pw]; q.dbias = r.grads[hh.pb]; q.R = hh.R; q.C = hh.C; q.Rb = hh.Rb; q.Rbp = hh.Rbp;
@@ -748,7 +751,7 @@ static int emn_backward(const Run& r, const BwdBufs& bb, const float* out, const
     GemmDW q;
     q.G = sc + bb.dgi; q.ldg = ih.Rp; q.Nn = ih.Rp; q.X = r.ws + L.emsg[t]; q.ldx = Hp; q.Kk = ih.Cp; q.M = E;
     q.dW = r.grads[ih.pw]; q.dbias = r.grads[ih.pb]; q.R = ih.R; q.C = ih.C; q.Rb = ih.Rb; q.Rbp = ih.Rbp;
-    q.rs = ih.rs; q.cs = ih.cs; q.scratch = sc + bb.dw;
+    q.rs = ih.rs; q.cs = ih.cs; q.scratch = sc + bb.dw; q.half_floats = bb.dw_half;
     GIB_TRY(gemm_dw(q, r.st));
     GIB_TRY(colsum_add(r.grads[hh.pb], sc + bb.dgh, hh.Rp, E, hh.R, hh.Rb, hh.Rbp, r.st));  // d b_hh; d W_hh = 0
     GemmNT p;
@@ -830,6 +833,7 @@ void make_bwd(const Run& r, BwdBufs& bb) {
   Bump bp;
   bb.GA = bp.take(big); bb.GB = bp.take(big); bb.T1 = bp.take(big); bb.T2 = bp.take(big);
   bb.dw = bp.take(dw);
+  bb.dw_half = dw / 2;          // gemm_dw alternates between two halves (helper side stream)
   bb.dh = bp.take(S * Hp); bb.dh2 = bp.take(S * Hp);
   bb.dmsum = bp.take(std::max(S, E) * (size_t)std::max(Mp, Hp));
   bb.dgi = bp.take(std::max(S, E) * 3 * Hp); bb.dgh = bp.take(std::max(S, E) * 3 * Hp);
@@ -850,7 +854,9 @@ int model_forward(const Run& r, float* out) {
   return r.pl.d.model == GIB_EMN ? emn_forward(r, out) : node_model_forward(r, out);
 }
 int model_backward(const Run& r, const BwdBufs& bb, const float* out, const float* dout) {
-  return r.pl.d.model == GIB_EMN ? emn_backward(r, bb, out, dout) : node_model_backward(r, bb, out, dout);
+  const int rc = r.pl.d.model == GIB_EMN ? emn_backward(r, bb, out, dout) : node_model_backward(r, bb, out, dout);
+  const int rj = dw_join(r.st);   // the last reduction job runs on the helper side stream: order it before the caller
+  return rc ? rc : rj;
 }
 
 }  // namespace gib

@@ -60,6 +60,7 @@ struct Layout {
 };
 
 struct BwdBufs {
+  size_t dw_half;
   size_t GA, GB, T1, T2, dw, dh, dh2, dmsum, dgi, dgh, dx0, dcat_att, dcat_add, dcat_conn, dgterm, dg;
   size_t dmem, dmem2, dEMx, dENx, dEMm, dENm, st3;
   size_t total;
