@@ -308,37 +308,22 @@ def run_b200_arm(args):
     lib.gib_profile_enable(0)
 
     # ---- timed region 2: end to end from pinned host buffers -------------------------------
-    # Every step: H2D of that step's inputs from pinned memory (on a copy stream, prefetched one step ahead, as a
-    # DataLoader with pin_memory does for the reference, Workflow.py:781-782) and D2H of the step's loss into pinned
-    # memory, read on the host one step later (so the host never stalls the launch queue).  All copies, the waits on
-    # them and the final synchronisation are inside the timed region.
-    copy_stream = torch.cuda.Stream(device=dev)
+    # Every step: H2D of that step's inputs from pinned host memory (non-blocking, on the step's stream, as the
+    # reference does at Workflow.py:781-782) and D2H of the step's loss into pinned memory; the host reads the value one
+    # step later so that it never stalls the launch queue (tools/e2e_probe.py: a blocking .item() per step costs 0.4 ms,
+    # the 5 MB of H2D 0.06 ms).  All copies and the final synchronisation are inside the timed region.
     loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
     loss_events = [torch.cuda.Event(), torch.cuda.Event()]
-
-    def prefetch():
-        with torch.cuda.stream(copy_stream):
-            batch = [t.to(dev, non_blocking=True) for t in pin]
-            ev = torch.cuda.Event()
-            ev.record(copy_stream)
-        return batch, ev
-
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    nxt = prefetch()
     host_losses = []
     for i in range(args.steps):
-        (n, e, t), ev = nxt
-        torch.cuda.current_stream(dev).wait_event(ev)
-        for x in (n, e, t):
-            x.record_stream(torch.cuda.current_stream(dev))
-        if i + 1 < args.steps:
-            nxt = prefetch()
+        n, e, t = (x.to(dev, non_blocking=True) for x in pin)
         loss_i = step(n, e, t)
         loss_host[i & 1].copy_(loss_i.detach(), non_blocking=True)      # D2H of this step's result
         loss_events[i & 1].record()
-        if i > 0:                                                        # read the previous step's loss on the host
+        if i > 0:                                                        # previous step's loss, read on the host
             loss_events[(i - 1) & 1].synchronize()
             host_losses.append(float(loss_host[(i - 1) & 1]))
     loss_events[(args.steps - 1) & 1].synchronize()
@@ -381,8 +366,8 @@ def run_b200_arm(args):
                        "bond_entries_per_batch": net.last_stats.get("entries")},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 + 64,
                     "ms_per_step": ms_e2e / args.steps,
-                    "how": "public module API; pinned host batch -> H2D on a copy stream (prefetch depth 1) -> step -> "
-                           "loss D2H to pinned memory, read on the host one step later; +64 B/step = K0 graph header"},
+                    "how": "public module API; pinned host batch -> non-blocking H2D -> step -> loss D2H to pinned memory, "
+                           "read on the host one step later; +64 B/step = K0 graph header"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "final_loss": final_loss}
     try:
         line["roofline_scatter"] = scatter_roofline(pk)
