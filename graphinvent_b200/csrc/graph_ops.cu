@@ -696,17 +696,6 @@ int mul_dselu(float* G, const float* d, const float* y, long long n, cudaStream_
   GIB_LAUNCH_CHECK();
   return 0;
 }
-__global__ void add_inplace_kernel(float* __restrict__ a, const float* __restrict__ b, long long n) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) a[i] += b[i];
-}
-int add_inplace(float* a, const float* b, long long n, cudaStream_t st) {
-  if (n <= 0) return 0;
-  add_inplace_kernel<<<GIB_1D(n, 256), 0, st>>>(a, b, n);
-  GIB_LAUNCH_CHECK();
-  return 0;
-}
-
 // ------------------------------------------------------------------------------------
 // parameter packing: reference-shaped weight [nblk*Rb, C] (element (r,c) at src[r*rs + c*cs])
 //   -> Wp  [nblk*Rbp, Cp]   zero padded, K-contiguous      (forward  B operand)

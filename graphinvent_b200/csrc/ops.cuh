@@ -28,7 +28,6 @@ int emn_input(float* X, int ld, const float* nodes, const float* edges, const in
 int emn_aggregate_fwd(float* msg, const float* EMx, const float* ENx, const float* EMm, const float* ENm, int ld, const int* ent_dst, const int* ent_src, const int* dst_ptr, long long E, cudaStream_t st);
 int emn_aggregate_bwd(float* dEMx, float* dENx, float* dEMm, float* dENm, float* st3, const float* dmsg, const float* EMx, const float* ENx, const float* EMm, const float* ENm, int ld, const GraphArrays& ga, long long E, cudaStream_t st);
 int mul_dselu(float* G, const float* d, const float* y, long long n, cudaStream_t st);
-int add_inplace(float* a, const float* b, long long n, cudaStream_t st);
 int pack_weight(float* Wp, float* WTp, float* bp, const float* W, const float* bias, long long rs, long long cs, int nblk, int Rb, int Rbp, int C, int Cp, int Ct, int Ctp, cudaStream_t st);
 
 }  // namespace gib

@@ -42,19 +42,6 @@ BIG = 1e6  # constants.big_positive / -big_negative (parameters/defaults.py)
 # --------------------------------------------------------------------------- #
 # hyper-parameter tuple (the subset of `constants` the hot path reads)
 # --------------------------------------------------------------------------- #
-HP_FIELDS = (
-    "model", "n_node_features", "n_edge_features", "max_n_nodes",
-    "len_f_add_per_node", "len_f_conn_per_node",
-    "hidden_node_features", "message_size", "message_passes",
-    "enn_hidden_dim", "enn_depth",
-    "msg_hidden_dim", "msg_depth", "att_hidden_dim", "att_depth",
-    "gather_width", "gather_att_hidden_dim", "gather_att_depth",
-    "gather_emb_hidden_dim", "gather_emb_depth",
-    "mlp1_hidden_dim", "mlp1_depth", "mlp2_hidden_dim", "mlp2_depth",
-    "edge_emb_size", "edge_emb_hidden_dim", "edge_emb_depth",
-)
-
-
 def make_constants(model="GGNN", **kw):
     """Build the namedtuple the reference constructors read (SURVEY §5 config row,
     `parameters/defaults.py:145-433` for the default values).  Contains every field
