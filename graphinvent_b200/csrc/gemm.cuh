@@ -17,6 +17,8 @@ enum Epi : int {
 struct GemmNT {
   const float* A = nullptr; int lda = 0;
   const float* B = nullptr; int ldb = 0;
+  const float* B_hi = nullptr;      // optional TF32 hi / lo planes of B (same shape and ldb): the tcgen05 kernel then
+  const float* B_lo = nullptr;      // loads them directly and only splits A on the fly
   float* C = nullptr; int ldc = 0;
   int M = 0, N = 0, K = 0;
   const float* bias = nullptr;

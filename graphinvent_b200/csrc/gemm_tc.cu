@@ -158,7 +158,8 @@ constexpr int MAXP = 4;   // independent GEMM problems per launch (grouped NT la
 
 struct Maps {   // TMA descriptors live in kernel-parameter space (__grid_constant__)
   CUtensorMap a[MAXP];
-  CUtensorMap b[MAXP];
+  CUtensorMap b[MAXP];      // raw fp32 B, or its TF32 hi plane when the caller supplies pre-split weights
+  CUtensorMap b_lo[MAXP];   // lo plane (pre-split weights only)
 };
 
 struct Params {
@@ -167,6 +168,7 @@ struct Params {
   // layer, different weights and row ranges) and for sibling MLPs of the readout.
   GemmNT g[MAXP];
   int m_tiles[MAXP], n_tiles[MAXP], k_blocks[MAXP], tile_begin[MAXP + 1];
+  int bsplit[MAXP];   // 1: B arrives as (hi, lo) planes from the packed arena -> only A is split in the kernel
   int nprob;
   // TN (weight-gradient) mode: P[z][n][k] = sum_{m in chunk z} G[m,n] X[m,k]; operands are the row-major
   // activations themselves (MN-major for the MMA), problem 0 only, g[0].C = split-K workspace
@@ -249,10 +251,12 @@ tc_gemm_nt_kernel(const __grid_constant__ Maps maps, const Params P) {
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* st = smem + stage * STAGE_BYTES;
-          mbar_arrive_expect_tx(&full_raw[stage], 2 * TILE_BYTES);
+          const bool presplit = !P.tn && P.bsplit[w.p];
+          mbar_arrive_expect_tx(&full_raw[stage], (presplit ? 3 : 2) * TILE_BYTES);
           if (!P.tn) {
             tma_load_2d(map_a, &full_raw[stage], st, kb * BKF, m0);
             tma_load_2d(map_b, &full_raw[stage], st + 2 * TILE_BYTES, kb * BKF, n0);
+            if (presplit) tma_load_2d(&maps.b_lo[w.p], &full_raw[stage], st + 3 * TILE_BYTES, kb * BKF, n0);
           } else {
             const int row = r0 + kb * BKF;           // 32 reduction rows per stage
 #pragma unroll
@@ -318,13 +322,14 @@ tc_gemm_nt_kernel(const __grid_constant__ Maps maps, const Params P) {
     int stage = 0;
     uint32_t phase = 0;
     for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
-      const int nkb = decode_item(P, item).nkb;
+      const Item wi = decode_item(P, item);
+      const int nkb = wi.nkb;
+      const int nops = (!P.tn && P.bsplit[wi.p]) ? 1 : 2;   // pre-split weights: only the A tile needs splitting
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(&full_raw[stage], phase);
         uint8_t* st = smem + stage * STAGE_BYTES;
         if (!(P.debug & 1))
-#pragma unroll
-        for (int op = 0; op < 2; ++op) {
+        for (int op = 0; op < nops; ++op) {
           float4* hi = reinterpret_cast<float4*>(st + op * 2 * TILE_BYTES);
           float4* lo = reinterpret_cast<float4*>(st + op * 2 * TILE_BYTES + TILE_BYTES);
 #pragma unroll
@@ -523,7 +528,11 @@ int gemm_nt_tc_group(const GemmNT* ps, int n, cudaStream_t st) {
     if (p.M <= 0 || p.N <= 0) continue;
     if (!tc_eligible(p)) { set_error("gemm_nt_tc: operands violate the TMA alignment contract"); return -2; }
     GIB_TRY(make_map(&maps.a[np], p.A, p.M, p.K, p.lda));
-    GIB_TRY(make_map(&maps.b[np], p.B, p.N, p.K, p.ldb));
+    const bool presplit = p.B_hi && p.B_lo && !(g_tc_debug & 16) && (reinterpret_cast<uintptr_t>(p.B_hi) & 15) == 0 &&
+                          (reinterpret_cast<uintptr_t>(p.B_lo) & 15) == 0;
+    GIB_TRY(make_map(&maps.b[np], presplit ? p.B_hi : p.B, p.N, p.K, p.ldb));
+    if (presplit) GIB_TRY(make_map(&maps.b_lo[np], p.B_lo, p.N, p.K, p.ldb));
+    P.bsplit[np] = presplit ? 1 : 0;
     P.g[np] = p;
     P.m_tiles[np] = ceil_div(p.M, BM);
     P.n_tiles[np] = ceil_div(p.N, BN);

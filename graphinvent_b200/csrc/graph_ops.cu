@@ -735,4 +735,60 @@ int pack_weight(float* Wp, float* WTp, float* bp, const float* W, const float* b
   return 0;
 }
 
+
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// all Linears of a model in ONE launch: the per-Linear descriptors travel as a kernel parameter (__grid_constant__)
+__global__ void __launch_bounds__(256) pack_all_kernel(const __grid_constant__ PackTable T, float* __restrict__ packed) {
+  __shared__ int s_idx;
+  if (threadIdx.x == 0) {
+    int i = 0;
+    while (i + 1 < T.n && blockIdx.x >= T.e[i + 1].blk_begin) ++i;
+    s_idx = i;
+  }
+  __syncthreads();
+  const PackEntry& E = T.e[s_idx];
+  const int Rp = E.nblk * E.Rbp;
+  const long long n1 = (long long)Rp * E.Cp, n2 = (long long)E.Ctp * Rp;
+  const long long base = (long long)(blockIdx.x - E.blk_begin) * 1024;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const long long idx = base + u * 256 + threadIdx.x;
+    if (idx < n1) {
+      const int pr = (int)(idx / E.Cp), c = (int)(idx % E.Cp);
+      const int g = pr / E.Rbp, rr = pr % E.Rbp;
+      float v = 0.f;
+      if (rr < E.Rb && c < E.C) v = E.W[(long long)(g * E.Rb + rr) * E.rs + c * E.cs];
+      packed[E.ow + idx] = v;
+      const float h = tf32_rna(v);
+      packed[E.ow_hi + idx] = h;
+      packed[E.ow_lo + idx] = tf32_rna(v - h);
+    } else if (idx < n1 + n2) {
+      const long long k = idx - n1;
+      const int c = (int)(k / Rp), pr = (int)(k % Rp);
+      const int g = pr / E.Rbp, rr = pr % E.Rbp;
+      float v = 0.f;
+      if (rr < E.Rb && c < E.Ct) v = E.W[(long long)(g * E.Rb + rr) * E.rs + c * E.cs];
+      packed[E.owt + k] = v;
+      const float h = tf32_rna(v);
+      packed[E.owt_hi + k] = h;
+      packed[E.owt_lo + k] = tf32_rna(v - h);
+    } else if (idx < n1 + n2 + Rp) {
+      const int pr = (int)(idx - n1 - n2);
+      const int g = pr / E.Rbp, rr = pr % E.Rbp;
+      packed[E.ob + pr] = (E.bias && rr < E.Rb) ? E.bias[g * E.Rb + rr] : 0.f;
+    }
+  }
+}
+int pack_all(const PackTable& T, float* packed, cudaStream_t st) {
+  if (T.n <= 0) return 0;
+  pack_all_kernel<<<T.total_blocks, 256, 0, st>>>(T, packed);
+  GIB_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace gib

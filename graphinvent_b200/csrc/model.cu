@@ -30,6 +30,11 @@ static void finish_lin(Plan& pl, Lin& l) {
   l.owt = pl.packed_floats; pl.packed_floats += (size_t)l.Ctp * l.Rp;
   l.ob = pl.packed_floats;  pl.packed_floats += (size_t)l.Rp;
   pl.packed_floats = (pl.packed_floats + 31) & ~(size_t)31;
+  l.ow_hi = pl.packed_floats;  pl.packed_floats += (size_t)l.Rp * l.Cp;
+  l.ow_lo = pl.packed_floats;  pl.packed_floats += (size_t)l.Rp * l.Cp;
+  l.owt_hi = pl.packed_floats; pl.packed_floats += (size_t)l.Ctp * l.Rp;
+  l.owt_lo = pl.packed_floats; pl.packed_floats += (size_t)l.Ctp * l.Rp;
+  pl.packed_floats = (pl.packed_floats + 31) & ~(size_t)31;
 }
 
 static Mlp add_mlp(Plan& pl, int fin, int hidden, int depth, int fout, int ct_first = -1) {
@@ -129,11 +134,28 @@ int build_plan(const gib_dims& d, Plan& pl) {
 }
 
 int pack_params(const Plan& pl, const float* const* params, float* packed, cudaStream_t st) {
-  for (const Lin& l : pl.lins) {
-    const float* W = params[l.pw] + l.src_off;
-    const float* b = l.pb >= 0 ? params[l.pb] : nullptr;
-    GIB_TRY(pack_weight(packed + l.ow, packed + l.owt, packed + l.ob, W, b, l.rs, l.cs, l.nblk, l.Rb, l.Rbp, l.C,
-                        l.Cp, l.Ct, l.Ctp, st));
+  if ((int)pl.lins.size() > kMaxPackEntries) {
+    set_error("pack_params: %d Linears exceed the descriptor table (%d)", (int)pl.lins.size(), kMaxPackEntries);
+    return -1;
+  }
+  {   // one launch for the whole model (52-67 Linears)
+    PackTable T;
+    T.n = (int)pl.lins.size();
+    unsigned blk = 0;
+    for (int i = 0; i < T.n; ++i) {
+      const Lin& l = pl.lins[i];
+      PackEntry& e = T.e[i];
+      e.W = params[l.pw] + l.src_off;
+      e.bias = l.pb >= 0 ? params[l.pb] : nullptr;
+      e.rs = l.rs; e.cs = l.cs; e.ow = (long long)l.ow; e.owt = (long long)l.owt; e.ob = (long long)l.ob;
+      e.ow_hi = (long long)l.ow_hi; e.ow_lo = (long long)l.ow_lo; e.owt_hi = (long long)l.owt_hi; e.owt_lo = (long long)l.owt_lo;
+      e.nblk = l.nblk; e.Rb = l.Rb; e.Rbp = l.Rbp; e.C = l.C; e.Cp = l.Cp; e.Ct = l.Ct; e.Ctp = l.Ctp;
+      e.blk_begin = blk;
+      const long long tot = (long long)l.Rp * l.Cp + (long long)l.Ctp * l.Rp + l.Rp;
+      blk += (unsigned)ceil_div_ll(tot, 1024);
+    }
+    T.total_blocks = blk;
+    return pack_all(T, packed, st);
   }
   return 0;
 }
@@ -269,7 +291,7 @@ static int mlp_forward(const Run& r, const Mlp& m, const float* X0, const MlpAct
     const Lin& L = r.pl.lins[m.first + l - 1];
     GemmNT p;
     p.A = x; p.lda = ldx;
-    p.B = r.packed + L.ow; p.ldb = L.Cp;
+    p.B = r.packed + L.ow; p.ldb = L.Cp; p.B_hi = r.packed + L.ow_hi; p.B_lo = r.packed + L.ow_lo;
     p.M = rows; p.N = L.Rp; p.K = L.Cp;
     p.bias = L.pb >= 0 ? r.packed + L.ob : nullptr;
     p.act = m.act; p.mode = EPI_ACT;
@@ -311,7 +333,7 @@ static int mlp_backward(const Run& r, const BwdBufs& bb, const Mlp& m, const flo
     if (l > 1 || dX0) {
       GemmNT p;
       p.A = G; p.lda = L.Rp;
-      p.B = r.packed + L.owt; p.ldb = L.Rp;
+      p.B = r.packed + L.owt; p.ldb = L.Rp; p.B_hi = r.packed + L.owt_hi; p.B_lo = r.packed + L.owt_lo;
       p.M = rows; p.N = L.Ctp; p.K = L.Rp;
       p.n_store = L.Ctp; p.n_valid = L.Ctp;
       p.work = 2.0 * rows * (double)L.R * L.Ct;
@@ -370,7 +392,7 @@ static int mlp_forward_multi(const Run& r, const MlpJob* jobs, int n) {
       GemmNT& p = ps[np];
       p = GemmNT();
       p.A = x[i]; p.lda = ldx[i];
-      p.B = r.packed + L.ow; p.ldb = L.Cp;
+      p.B = r.packed + L.ow; p.ldb = L.Cp; p.B_hi = r.packed + L.ow_hi; p.B_lo = r.packed + L.ow_lo;
       p.M = j.rows; p.N = L.Rp; p.K = L.Cp;
       p.bias = L.pb >= 0 ? r.packed + L.ob : nullptr;
       p.act = j.m->act; p.mode = EPI_ACT;
@@ -428,6 +450,7 @@ static int mlp_backward_multi(const Run& r, const BwdBufs& bb, const MlpBwdJob* 
         GemmNT& p = ps[np];
         p = GemmNT();
         p.A = G[i]; p.lda = L.Rp; p.B = r.packed + L.owt; p.ldb = L.Rp;
+        p.B_hi = r.packed + L.owt_hi; p.B_lo = r.packed + L.owt_lo;
         p.M = j.rows; p.N = L.Ctp; p.K = L.Rp; p.n_store = L.Ctp; p.n_valid = L.Ctp;
         p.work = 2.0 * j.rows * (double)L.R * L.Ct;
         p.C = (G[i] == ping[i]) ? pong[i] : ping[i]; p.ldc = L.Ctp;
@@ -436,6 +459,7 @@ static int mlp_backward_multi(const Run& r, const BwdBufs& bb, const MlpBwdJob* 
       } else if (j.dX0) {   // input gradients may chain through a shared buffer (aux): keep them in order
         GemmNT p1;
         p1.A = G[i]; p1.lda = L.Rp; p1.B = r.packed + L.owt; p1.ldb = L.Rp;
+        p1.B_hi = r.packed + L.owt_hi; p1.B_lo = r.packed + L.owt_lo;
         p1.M = j.rows; p1.N = L.Ctp; p1.K = L.Rp; p1.n_store = L.Ctp; p1.n_valid = L.Ctp;
         p1.work = 2.0 * j.rows * (double)L.R * L.Ct;
         p1.C = j.dX0; p1.ldc = j.ld_dx;
@@ -603,11 +627,13 @@ static int node_model_forward(const Run& r, float* out) {
       GemmNT ps[2];
       GemmNT& p = ps[0];
       p.A = r.ws + L.msum[t]; p.lda = Mp; p.B = r.packed + ih.ow; p.ldb = ih.Cp; p.C = r.ws + L.gi[t]; p.ldc = ih.Rp;
+      p.B_hi = r.packed + ih.ow_hi; p.B_lo = r.packed + ih.ow_lo;
       p.M = (int)S; p.N = ih.Rp; p.K = ih.Cp; p.bias = r.packed + ih.ob; p.act = ACT_NONE; p.mode = EPI_ACT;
       p.n_store = p.n_valid = ih.Rp; p.work = 2.0 * S * (double)ih.R * ih.C;
       GemmNT& q2 = ps[1];
       q2 = p;
       q2.A = h; q2.lda = Hp; q2.B = r.packed + hh.ow; q2.ldb = hh.Cp; q2.C = r.ws + L.gh[t]; q2.ldc = hh.Rp;
+      q2.B_hi = r.packed + hh.ow_hi; q2.B_lo = r.packed + hh.ow_lo;
       q2.N = hh.Rp; q2.K = hh.Cp; q2.bias = r.packed + hh.ob; q2.n_store = q2.n_valid = hh.Rp;
       q2.work = 2.0 * S * (double)hh.R * hh.C;
       GIB_TRY(gemm_nt_group(ps, 2, r.st));
@@ -646,13 +672,17 @@ static int node_model_backward(const Run& r, const BwdBufs& bb, const float* out
       GemmNT ps[2];
       GemmNT& p = ps[0];
       p.A = sc + bb.dgi; p.lda = ih.Rp; p.B = r.packed + ih.owt; p.ldb = ih.Rp; p.C = sc + bb.dmsum; p.ldc = Mp;
+      p.B_hi = r.packed + ih.owt_hi; p.B_lo = r.packed + ih.owt_lo;
       p.M = (int)S; p.N = ih.Ctp; p.K = ih.Rp; p.mode = EPI_ACT; p.act = ACT_NONE; p.n_store = p.n_valid = ih.Ctp;
       p.work = 2.0 * S * (double)ih.R * ih.C;
       GemmNT& q2 = ps[1];
       q2.A = sc + bb.dgh; q2.lda = hh.Rp; q2.B = r.packed + hh.owt; q2.ldb = hh.Rp; q2.C = dh; q2.ldc = Hp;
+      q2.B_hi = r.packed + hh.owt_hi; q2.B_lo = r.packed + hh.owt_lo;
       q2.M = (int)S; q2.N = hh.Ctp; q2.K = hh.Rp; q2.mode = EPI_ADD; q2.aux = dh_dir; q2.ldaux = Hp;
       q2.n_store = q2.n_valid = hh.Ctp; q2.work = 2.0 * S * (double)hh.R * hh.C;
-      GIB_TRY(gemm_nt_group(ps, 2, r.st));
+      // h[0] is the zero-padded input (summation_mpnn.py:121-125): nothing consumes d h[0], so at t == 0 the dh GEMM,
+      // the first-layer input gradients of the message MLPs and their scatter are skipped
+      GIB_TRY(gemm_nt_group(ps, t == 0 ? 1 : 2, r.st));
     }
     // through the aggregation into the per-bond message MLPs
     float* T1 = sc + bb.T1;
@@ -672,22 +702,23 @@ static int node_model_backward(const Run& r, const BwdBufs& bb, const float* out
       MlpBwdJob jobs[4];
       for (int g = 0; g < r.ngroups; ++g) {
         const size_t ro = (size_t)r.tb[g];
-        jobs[g] = MlpBwdJob{&pl.msg[g], r.ws + L.x0[t], &L.msg[t], r.tb[g], r.tc[g], T1 + ro * Mp, dx0 + ro * Hp, Hp,
-                            nullptr};
+        jobs[g] = MlpBwdJob{&pl.msg[g], r.ws + L.x0[t], &L.msg[t], r.tb[g], r.tc[g], T1 + ro * Mp,
+                            t == 0 ? nullptr : dx0 + ro * Hp, Hp, nullptr};
       }
       GIB_TRY(mlp_backward_multi(r, bb, jobs, r.ngroups));
       if (d.model == GIB_ATTGGNN) {
         for (int g = 0; g < r.ngroups; ++g) {
           const size_t ro = (size_t)r.tb[g];
-          jobs[g] = MlpBwdJob{&pl.att[g], r.ws + L.x0[t], &L.att[t], r.tb[g], r.tc[g], T2 + ro * Mp, dx0 + ro * Hp,
-                              Hp, dx0 + ro * Hp};
+          jobs[g] = MlpBwdJob{&pl.att[g], r.ws + L.x0[t], &L.att[t], r.tb[g], r.tc[g], T2 + ro * Mp,
+                              t == 0 ? nullptr : dx0 + ro * Hp, Hp, dx0 + ro * Hp};
         }
         GIB_TRY(mlp_backward_multi(r, bb, jobs, r.ngroups));
       }
     }
     // dh[t][src] += (w) dX0   -- deterministic gather-reduce over the by-source CSR
-    GIB_TRY(scatter_sum(dh, dx0, Hp, r.ga.src_ptr, r.ga.src_ent, d.model == GIB_GGNN ? r.w() : nullptr, 1, S,
-                        r.st));
+    if (t > 0)
+      GIB_TRY(scatter_sum(dh, dx0, Hp, r.ga.src_ptr, r.ga.src_ent, d.model == GIB_GGNN ? r.w() : nullptr, 1, S,
+                          r.st));
   }
   return 0;
 }

@@ -21,6 +21,7 @@ struct Lin {
   int Ct;                 // leading input columns kept in the transposed copy
   int Rbp, Rp, Cp, Ctp;   // padded extents
   size_t ow, owt, ob;     // float offsets of Wp [Rp, Cp], WTp [Ctp, Rp], bp [Rp] in the packed arena
+  size_t ow_hi, ow_lo, owt_hi, owt_lo;   // TF32 hi / lo planes of Wp and WTp (pre-split B operands of the tcgen05 GEMM)
 };
 
 struct Mlp {

@@ -5,6 +5,16 @@
 
 namespace gib {
 
+constexpr int kMaxPackEntries = 96;
+struct PackEntry {   // one reference weight (+bias) -> its padded / transposed copies in the packed arena
+  const float* W; const float* bias;
+  long long rs, cs, ow, owt, ob, ow_hi, ow_lo, owt_hi, owt_lo;
+  int nblk, Rb, Rbp, C, Cp, Ct, Ctp;
+  unsigned blk_begin;
+};
+struct PackTable { int n; unsigned total_blocks; PackEntry e[kMaxPackEntries]; };
+int pack_all(const PackTable& T, float* packed, cudaStream_t st);
+
 int concat2(float* dst, int ldd, const float* a, int lda, int wa, const float* b, int ldb, int wb, long long rows, cudaStream_t st);
 int concat_flat(float* dst, int ldd, const float* f1, int ldf, int N, int fa, const float* g, int ldg, int W, int B, cudaStream_t st);
 int unflatten_dact(float* G, int ldf, const float* dcat, int ldd, const float* f1, int N, int fa, long long S, cudaStream_t st);
