@@ -328,29 +328,32 @@ tc_gemm_nt_kernel(const __grid_constant__ Maps maps, const Params P) {
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(&full_raw[stage], phase);
         uint8_t* st = smem + stage * STAGE_BYTES;
-        if (!(P.debug & 1))
-        for (int op = 0; op < nops; ++op) {
-          float4* hi = reinterpret_cast<float4*>(st + op * 2 * TILE_BYTES);
-          float4* lo = reinterpret_cast<float4*>(st + op * 2 * TILE_BYTES + TILE_BYTES);
+        if (!(P.debug & 1)) {
+          auto split_tile = [&](int op) {
+            float4* hi = reinterpret_cast<float4*>(st + op * 2 * TILE_BYTES);
+            float4* lo = reinterpret_cast<float4*>(st + op * 2 * TILE_BYTES + TILE_BYTES);
 #pragma unroll
-          for (int i = 0; i < TILE_BYTES / 16 / 128; ++i) {
-            const int c = t + i * 128;
-            const float4 v = hi[c];
-            float4 h, l;
-            if (SPLIT == 1) {    // round-to-nearest split: 3 conversions per element, smallest error
-              h.x = __uint_as_float(to_tf32(v.x)); l.x = __uint_as_float(to_tf32(v.x - h.x));
-              h.y = __uint_as_float(to_tf32(v.y)); l.y = __uint_as_float(to_tf32(v.y - h.y));
-              h.z = __uint_as_float(to_tf32(v.z)); l.z = __uint_as_float(to_tf32(v.z - h.z));
-              h.w = __uint_as_float(to_tf32(v.w)); l.w = __uint_as_float(to_tf32(v.w - h.w));
-            } else {             // hi = top 19 bits (exact tf32), lo = x - hi (exact in fp32; the MMA reads its top 19 bits)
-              h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
-              h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
-              h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
-              h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
+            for (int i = 0; i < TILE_BYTES / 16 / 128; ++i) {
+              const int c = t + i * 128;
+              const float4 v = hi[c];
+              float4 h, l;
+              if (SPLIT == 1) {    // round-to-nearest split: 3 conversions per element, smallest error
+                h.x = __uint_as_float(to_tf32(v.x)); l.x = __uint_as_float(to_tf32(v.x - h.x));
+                h.y = __uint_as_float(to_tf32(v.y)); l.y = __uint_as_float(to_tf32(v.y - h.y));
+                h.z = __uint_as_float(to_tf32(v.z)); l.z = __uint_as_float(to_tf32(v.z - h.z));
+                h.w = __uint_as_float(to_tf32(v.w)); l.w = __uint_as_float(to_tf32(v.w - h.w));
+              } else {             // hi = top 19 bits (exact tf32), lo = x - hi (exact in fp32; the MMA reads its top 19 bits)
+                h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
+                h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
+                h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
+                h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
+              }
+              hi[c] = h;
+              lo[c] = l;
             }
-            hi[c] = h;
-            lo[c] = l;
-          }
+          };
+          split_tile(0);
+          if (nops == 2) split_tile(1);
         }
         fence_proxy_async();           // generic-proxy smem writes -> visible to the tensor-core (async) proxy
         mbar_arrive(&full_split[stage]);
