@@ -27,6 +27,75 @@ def test_trace_fixture_is_self_consistent():
     assert z["properly_terminated"][:n_gen].sum() >= n_gen // 3  # trained checkpoint: most molecules terminate properly
 
 
+def test_generation_oracle_replays_the_reference_trace_bit_exactly():
+    """pins oracle/generation_oracle.py to the unmodified reference generator (CPU, no GPU needed)"""
+    from oracle import generation_oracle as G
+    z = _trace()
+    B = int(z["batch"])
+    st = G.GenerationState(B, 13, 5, 3, 3)
+    for rnd, (a, l) in enumerate(zip(z["actions"], z["likelihoods"])):
+        G.generation_round(st, rnd, a, l)
+    assert st.n_generated == int(z["n_generated"])
+    assert (st.generated_nodes.astype(np.int8) == z["generated_nodes"]).all()
+    assert (st.generated_edges.astype(np.int8) == z["generated_edges"]).all()
+    assert (st.generated_n_nodes == z["generated_n_nodes"]).all()
+    assert (st.generated_likelihoods == z["generated_likelihoods"]).all()
+    assert (st.properly_terminated == z["properly_terminated"]).all()
+    assert (st.nodes.astype(np.int8) == z["final_nodes"]).all() and (st.edges.astype(np.int8) == z["final_edges"]).all()
+    assert (st.n_nodes.astype(np.int8) == z["final_n_nodes"]).all() and (st.likelihoods == z["final_likelihoods"]).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,N,A,CH,Ef,B", [(0, 13, 5, 3, 3, 200), (1, 5, 2, 1, 2, 64), (2, 38, 9, 3, 3, 96)])
+def test_round_kernels_match_the_oracle_on_random_action_streams(seed, N, A, CH, Ef, B):
+    """uniformly random actions hit every validity rule (bond to a missing atom, first atom off slot 0, full graph,
+    connect in an empty graph, self loop, double bond) far more often than a trained model does"""
+    from graphinvent_b200.config import make_constants
+    from graphinvent_b200.generation import GraphGenerator
+    from oracle import generation_oracle as G
+    rng = np.random.default_rng(seed)
+    C = make_constants("GGNN", max_n_nodes=N, n_node_features=A + CH, n_edge_features=Ef,
+                       len_f_add_per_node=A * CH * Ef, len_f_conn_per_node=Ef)
+    apd = N * (A * CH * Ef + Ef) + 1
+    rounds = 2 * N - 1
+    acts = rng.integers(0, apd, (rounds, B)).astype(np.int32)
+    # bias the stream towards valid growth so that graphs also get large: half of the draws add to the newest atom
+    grow = rng.random((rounds, B)) < 0.5
+    liks = rng.random((rounds, B)).astype(np.float32)
+    st = G.GenerationState(B, N, A, CH, Ef)
+    gen = GraphGenerator(model=None, batch_size=B, constants=C, n_atom_types=A, n_formal_charge=CH)
+    for rnd in range(rounds):
+        if st.n_generated > B:          # a round writes at most B-1 graphs: stay inside the 2B output buffers
+            break
+        a = acts[rnd].copy()
+        n_now = st.n_nodes.copy()
+        bt = np.maximum(n_now - 1, 0)
+        a[grow[rnd]] = ((bt * A + rng.integers(0, A, B)) * CH + rng.integers(0, CH, B))[grow[rnd]] * Ef + \
+            rng.integers(0, Ef, B)[grow[rnd]]
+        G.generation_round(st, rnd, a, liks[rnd])
+        # drive the kernels one round at a time through the same entry point build_graphs() uses
+        import ctypes
+        from graphinvent_b200._lib import check, lib
+        P = lambda t: ctypes.c_void_p(t.data_ptr())
+        ad, ld = torch.from_numpy(a).cuda(), torch.from_numpy(liks[rnd]).cuda()
+        check(lib.gib_generation_round(B, N, A + CH, Ef, A, CH, rnd, P(ad), P(ld), P(gen.nodes), P(gen.edges),
+                                       P(gen.n_nodes), P(gen.likelihoods), P(gen.generated_nodes),
+                                       P(gen.generated_edges), P(gen.generated_n_nodes), P(gen.generated_likelihoods),
+                                       P(gen.properly_terminated), gen.capacity, P(gen._counters), P(gen._scratch),
+                                       ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "round")
+        assert int(gen._counters[0].item()) == st.n_generated, rnd
+        assert (gen.nodes.cpu().numpy() == st.nodes).all(), rnd
+        assert (gen.edges.cpu().numpy() == st.edges).all(), rnd
+        assert (gen.n_nodes.cpu().numpy() == st.n_nodes).all(), rnd
+        assert (gen.likelihoods.cpu().numpy() == st.likelihoods).all(), rnd
+    assert (gen.generated_nodes.cpu().numpy() == st.generated_nodes).all()
+    assert (gen.generated_edges.cpu().numpy() == st.generated_edges).all()
+    assert (gen.generated_n_nodes.cpu().numpy() == st.generated_n_nodes).all()
+    assert (gen.generated_likelihoods.cpu().numpy() == st.generated_likelihoods).all()
+    assert (gen.properly_terminated.cpu().numpy() == st.properly_terminated).all()
+    assert st.n_generated > B // 4
+
+
 @pytest.mark.gpu
 def test_replay_reproduces_the_reference_generator_bit_exactly():
     from graphinvent_b200.config import make_constants
