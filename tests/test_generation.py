@@ -45,11 +45,32 @@ def test_generation_oracle_replays_the_reference_trace_bit_exactly():
     assert (st.n_nodes.astype(np.int8) == z["final_n_nodes"]).all() and (st.likelihoods == z["final_likelihoods"]).all()
 
 
+def _action_stream(rng, st, apd, len_add):
+    """per slot, mostly a valid-looking add (bond to an existing atom; overflows once the graph is full) so graphs grow
+    to max_n_nodes; the remaining 0.6/N of the draws are connects among existing atoms (valid, self loop or duplicate
+    bond), connects to a random position (missing atom), terminates and uniformly random indices"""
+    B, N, A, CH, Ef = st.B, st.N, st.A, st.CH, st.Ef
+    q = 0.6 / N
+    u = rng.random(B)
+    n = st.n_nodes
+    big = rng.integers(0, 1 << 30, B)
+    bond_to = np.where(n > 0, big % np.maximum(n, 1), 0)
+    first_bond = np.where((n == 0) & (rng.random(B) < 0.9), 0, rng.integers(0, Ef, B))
+    add = ((bond_to * A + rng.integers(0, A, B)) * CH + rng.integers(0, CH, B)) * Ef + np.where(n == 0, first_bond, rng.integers(0, Ef, B))
+    conn_in = len_add + bond_to * Ef + rng.integers(0, Ef, B)
+    conn_any = len_add + rng.integers(0, N, B) * Ef + rng.integers(0, Ef, B)
+    a = np.where(u < 1 - q, add,
+                 np.where(u < 1 - 0.5 * q, conn_in,
+                          np.where(u < 1 - 0.3 * q, conn_any, np.where(u < 1 - 0.15 * q, apd - 1, rng.integers(0, apd, B)))))
+    return a.astype(np.int32)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("seed,N,A,CH,Ef,B", [(0, 13, 5, 3, 3, 200), (1, 5, 2, 1, 2, 64), (2, 38, 9, 3, 3, 96)])
 def test_round_kernels_match_the_oracle_on_random_action_streams(seed, N, A, CH, Ef, B):
-    """uniformly random actions hit every validity rule (bond to a missing atom, first atom off slot 0, full graph,
-    connect in an empty graph, self loop, double bond) far more often than a trained model does"""
+    """a synthetic action stream that grows graphs up to max_n_nodes and hits every validity rule (bond to a missing
+    atom, first atom off slot 0, full graph, connect in an empty graph, self loop, double bond) far more often than
+    a trained model does"""
     from graphinvent_b200.config import make_constants
     from graphinvent_b200.generation import GraphGenerator
     from oracle import generation_oracle as G
@@ -58,20 +79,14 @@ def test_round_kernels_match_the_oracle_on_random_action_streams(seed, N, A, CH,
                        len_f_add_per_node=A * CH * Ef, len_f_conn_per_node=Ef)
     apd = N * (A * CH * Ef + Ef) + 1
     rounds = 2 * N - 1
-    acts = rng.integers(0, apd, (rounds, B)).astype(np.int32)
-    # bias the stream towards valid growth so that graphs also get large: half of the draws add to the newest atom
-    grow = rng.random((rounds, B)) < 0.5
     liks = rng.random((rounds, B)).astype(np.float32)
     st = G.GenerationState(B, N, A, CH, Ef)
     gen = GraphGenerator(model=None, batch_size=B, constants=C, n_atom_types=A, n_formal_charge=CH)
+    len_add = N * A * CH * Ef
     for rnd in range(rounds):
         if st.n_generated > B:          # a round writes at most B-1 graphs: stay inside the 2B output buffers
             break
-        a = acts[rnd].copy()
-        n_now = st.n_nodes.copy()
-        bt = np.maximum(n_now - 1, 0)
-        a[grow[rnd]] = ((bt * A + rng.integers(0, A, B)) * CH + rng.integers(0, CH, B))[grow[rnd]] * Ef + \
-            rng.integers(0, Ef, B)[grow[rnd]]
+        a = _action_stream(rng, st, apd, len_add)
         G.generation_round(st, rnd, a, liks[rnd])
         # drive the kernels one round at a time through the same entry point build_graphs() uses
         import ctypes
@@ -93,7 +108,7 @@ def test_round_kernels_match_the_oracle_on_random_action_streams(seed, N, A, CH,
     assert (gen.generated_n_nodes.cpu().numpy() == st.generated_n_nodes).all()
     assert (gen.generated_likelihoods.cpu().numpy() == st.generated_likelihoods).all()
     assert (gen.properly_terminated.cpu().numpy() == st.properly_terminated).all()
-    assert st.n_generated > B // 4
+    assert st.n_generated > B // 4 and int(st.generated_n_nodes.max()) == N     # the stream filled graphs completely
 
 
 @pytest.mark.gpu
