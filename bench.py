@@ -246,7 +246,11 @@ def run_b200_arm(args):
     torch.manual_seed(0)                      # identical random-init replicas on every rank
     net = mpnn.create(C).to(dev)
     hook = parallel.GradAllReduce(net) if world > 1 else None
-    opt = torch.optim.Adam(net.parameters(), lr=1e-4, fused=True)
+    if args.optimizer == "flat":              # one gib_adam_step launch over the flat parameter / gradient buckets
+        from graphinvent_b200.optim import FlatAdam
+        opt = FlatAdam(net.parameters(), lr=1e-4)
+    else:
+        opt = torch.optim.Adam(net.parameters(), lr=1e-4, fused=True)
     nodes, edges, target = nodes_h.to(dev), edges_h.to(dev), target_h.to(dev)
     pin = [t.pin_memory() for t in (nodes_h, edges_h, target_h)]
     h2d = sum(t.numel() * t.element_size() for t in pin)
@@ -360,6 +364,7 @@ def run_b200_arm(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": CONFIGS[args.config][5], "name": args.config, "per_gpu_batch": B,
                        "global_batch": B * world, "step": "fwd+kl_loss+bwd" + ("+allreduce" if world > 1 else "") + "+adam",
+                       "optimizer": "graphinvent_b200.optim.FlatAdam (1 launch)" if args.optimizer == "flat" else "torch.optim.Adam(fused=True)",
                        "parallelism": f"dp{world}", "weights": "random init (reference initialisers: xavier-uniform MLPs, PyTorch-default GRU), torch.manual_seed(0)",
                        "l2": "per-step working set (saved activations + packed weights, "
                              f"{net.last_stats.get('workspace_bytes', 0) / 1e6:.0f} MB) exceeds the 126 MB L2; no explicit flush",
@@ -408,6 +413,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="C2", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--optimizer", default="torch", choices=["flat", "torch"])
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = args.steps if args.steps is not None else 5

@@ -13,6 +13,7 @@ c_p = ctypes.c_void_p
 c_i = ctypes.c_int
 c_ll = ctypes.c_longlong
 c_f = ctypes.c_float
+c_d = ctypes.c_double
 c_sz = ctypes.c_size_t
 
 
@@ -56,6 +57,7 @@ _PROTOS = {
     "gib_seg_softmax": (c_i, [c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_ll, c_p]),
     "gib_gru_gates": (c_i, [c_p, c_p, c_p, c_p, c_i, c_p, c_ll, c_p]),
     "gib_graph_gather": (c_i, [c_p, c_p, c_p, c_p, c_i, c_p, c_i, c_i, c_f, c_p]),
+    "gib_adam_step": (c_i, [c_p, c_p, c_p, c_p, c_ll, c_ll, c_d, c_d, c_d, c_d, c_d, c_d, c_p]),
     "gib_sample_actions": (c_i, [c_p, c_i, c_i, c_p, c_p, c_p, c_p]),
     "gib_generation_scratch_bytes": (c_sz, [c_i]),
     "gib_generation_round": (c_i, [c_i] * 7 + [c_p] * 11 + [c_i, c_p, c_p, c_p]),

@@ -61,10 +61,18 @@ def _ptr_table(tensors):
     return arr
 
 
+_weights_epoch = [0]
+
+
+def invalidate_packed_weights():
+    """for writers that bypass autograd's version counters (the flat Adam kernel writes through raw pointers)"""
+    _weights_epoch[0] += 1
+
+
 def packed_weights(model, d, params):
     """Zero-padded / transposed weight arena, rebuilt only when a parameter changed
     (keyed on data_ptr + in-place version counter, so generation re-uses it every round)."""
-    key = tuple((p.data_ptr(), p._version) for p in params)
+    key = (_weights_epoch[0],) + tuple((p.data_ptr(), p._version) for p in params)
     if model._packed is not None and model._packed_key == key:
         return model._packed
     if model._packed_key is None or len(model._packed_key) != len(key):

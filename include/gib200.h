@@ -113,6 +113,16 @@ int gib_model_backward(const gib_dims* d, const int* hdr_host, const float* node
 int gib_kl_loss_fwd_bwd(const float* out, const float* target, int B, int apd, float grad_scale,
                         float* loss_rows, float* dout, gib_stream stream);
 
+/* ---- flat-bucket Adam step: replaces torch.optim.Adam.step() on the model parameters (constructed at
+ *      Workflow.py:191,221,245, stepped at Workflow.py:795-796; same update rule, L2 weight decay, no amsgrad)
+ *      with ONE launch over contiguous params / grads / exp_avg / exp_avg_sq of n floats.  `step` is the
+ *      1-based update count (bias corrections are evaluated in double on the host, as the reference does in
+ *      Python floats); grads are multiplied by grad_scale first (1/world when the bucket holds an all-reduce
+ *      sum).  The four buffers must share their address modulo 16 bytes. ------------------------------------ */
+int gib_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,
+                  long long step, double lr, double beta1, double beta2, double eps, double weight_decay,
+                  double grad_scale, gib_stream stream);
+
 /* ---- single kernels (unit tests, ncu evidence, reuse) --------------------------------- */
 /* Y = act(X W^T + b); X [M, ldx], W packed [Np, Kp] (ldw), Y [M, ldy]; act 0 none / 1 selu / 2 tanh */
 int gib_linear_fwd(const float* X, int ldx, const float* W, int ldw, const float* bias, float* Y, int ldy,
