@@ -413,7 +413,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="C2", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--optimizer", default="torch", choices=["flat", "torch"])
+    ap.add_argument("--optimizer", default="flat", choices=["flat", "torch"],
+                    help="flat = graphinvent_b200.optim.FlatAdam (one launch); torch = torch.optim.Adam(fused=True)")
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = args.steps if args.steps is not None else 5

@@ -27,7 +27,7 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
   p = fmaf(-s.step_size, m / denom, p);
 }
 
-__global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g,
+__global__ void __launch_bounds__(256, 6) adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                         float* __restrict__ m, float* __restrict__ v, long long n,
                                                         long long head, AdamScalars s) {
   // [0, head) scalar prologue up to 16-byte alignment, then float4 body, then scalar tail
@@ -87,7 +87,7 @@ extern "C" int gib_adam_step(float* params, const float* grads, float* exp_avg, 
   if (head > n) head = n;
   const long long work = (n + 3) / 4;
   long long blocks = (work + 255) / 256;
-  const long long cap = 148LL * 8;   // 8 resident CTAs of 256 threads per SM
+  const long long cap = 148LL * 6;   // one wave: 6 resident CTAs of 256 threads per SM (40 registers)
   if (blocks > cap) blocks = cap;
   adam_flat_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(params, grads, exp_avg,
                                                                                          exp_avg_sq, n, head, s);
