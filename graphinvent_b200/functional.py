@@ -36,6 +36,12 @@ def make_dims(model, batch):
     return d
 
 
+def dims_key(model, batch):
+    """hashable copy of the `gib_dims` a model would be run with (two models with equal keys can share K0's output)"""
+    d = make_dims(model, batch)
+    return tuple(getattr(d, name) for name, _ in Dims._fields_)
+
+
 def _require_cuda(*tensors):
     for t in tensors:
         if not t.is_cuda:
@@ -86,11 +92,15 @@ def packed_weights(model, d, params):
 
 
 class GraphBatch:
-    """Device-side bond-entry lists + CSR of one batch (output of K0) and its host header."""
-    __slots__ = ("hdr", "hdr_np", "buf", "n_entries", "n_rows", "flags")
+    """Device-side bond-entry lists + CSR of one batch (output of K0) and its host header.
+    It depends on the batch (B, N, Ef, the edges tensor) and on whether the model is the EMN, not on the weights:
+    two models of one family can share it (`build_graph`, SURVEY.md 8f rank 4: agent + prior of the RL rollout)."""
+    __slots__ = ("hdr", "hdr_np", "buf", "n_entries", "n_rows", "flags", "key", "source")
 
     def __init__(self, d, edges):
         dev = edges.device
+        self.key = (d.B, d.N, d.Ef, d.model)
+        self.source = (edges.data_ptr(), edges._version)
         st = _stream(dev)
         cws = torch.empty(lib.gib_graph_count_ws_bytes(ctypes.byref(d)), dtype=_u8, device=dev)
         check(lib.gib_graph_count(ctypes.byref(d), _ptr(edges), _ptr(cws), st), "gib_graph_count")
@@ -103,6 +113,9 @@ class GraphBatch:
         self.buf = torch.empty(max(256, lib.gib_graph_bytes(ctypes.byref(d), self.hdr)), dtype=_u8, device=dev)
         check(lib.gib_graph_fill(ctypes.byref(d), _ptr(edges), _ptr(cws), self.hdr, _ptr(self.buf), st),
               "gib_graph_fill")
+
+    def matches(self, d, edges):
+        return self.key == (d.B, d.N, d.Ef, d.model) and self.source == (edges.data_ptr(), edges._version)
 
     def array(self, d, which, count, dtype=torch.int32):
         """view of one internal array (tests): which = 0 ent_src .. 6 src_ent (include/gib200.h)"""
@@ -118,7 +131,11 @@ class _MPNNFunction(torch.autograd.Function):
         B = nodes.shape[0]
         d = make_dims(model, B)
         st = _stream(dev)
-        graph = GraphBatch(d, edges)
+        graph = getattr(model, "_graph_in", None)       # a CSR shared between models (mpnn_forward(graph=...))
+        if graph is None:
+            graph = GraphBatch(d, edges)
+        elif not graph.matches(d, edges):
+            raise ValueError("the shared GraphBatch was built for another batch, model family or edges tensor")
         packed = packed_weights(model, d, params)
         ws_bytes = lib.gib_model_workspace_bytes(ctypes.byref(d), graph.hdr)
         if ws_bytes == 0:
@@ -156,7 +173,17 @@ class _MPNNFunction(torch.autograd.Function):
         return (None, None, None, *views)
 
 
-def mpnn_forward(model, nodes, edges):
+def build_graph(model, edges):
+    """K0 once for several forward passes over the same batch (same model family): pass the result as
+    `model(nodes, edges, graph=...)`.  `edges` must be the contiguous float32 tensor that is then fed to the models,
+    unmodified in between."""
+    _require_cuda(edges)
+    if edges.dim() != 4 or edges.dtype != torch.float32 or not edges.is_contiguous():
+        raise ValueError("build_graph expects a contiguous float32 edges tensor [B,N,N,Ef]")
+    return GraphBatch(make_dims(model, edges.shape[0]), edges)
+
+
+def mpnn_forward(model, nodes, edges, graph=None):
     _require_cuda(nodes, edges)
     params = list(model.parameters())
     _require_cuda(*params)
@@ -164,10 +191,14 @@ def mpnn_forward(model, nodes, edges):
         raise ValueError("expected nodes [B,N,F] and edges [B,N,N,Ef]")
     nodes = nodes.contiguous().float()
     edges = edges.contiguous().float()
-    if torch.is_grad_enabled() and any(p.requires_grad for p in params):
-        return _MPNNFunction.apply(model, nodes, edges, *params)
-    with torch.no_grad():
-        return _MPNNFunction.apply(model, nodes, edges, *[p.detach() for p in params])
+    model._graph_in = graph
+    try:
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            return _MPNNFunction.apply(model, nodes, edges, *params)
+        with torch.no_grad():
+            return _MPNNFunction.apply(model, nodes, edges, *[p.detach() for p in params])
+    finally:
+        model._graph_in = None
 
 
 # ------------------------------------------------------------------------------------------

@@ -10,6 +10,11 @@ finished; `sample()` returns the finished tensors and likelihood summaries.  Con
 The sampler draws with inverse-CDF on `torch.rand` uniforms (same distribution as `Multinomial(1, probs)`, different
 RNG stream); `build_graphs(replay=...)` replays recorded draws instead, which is how the parity tests pin the state
 machine bit-exactly against a trace of the unmodified reference.
+
+`GraphGeneratorRL` is the twin used by the reinforcement-learning loop (reference GraphGeneratorRL.py:25-172):
+two models are evaluated on every round -- the sampling "agent" and a second model whose probability of the SAME
+action is recorded -- and, unlike plain generation, autograd runs through the whole rollout
+(`Workflow.learning_step`, Workflow.py:569-612, back-propagates a loss on the summed likelihoods).
 """
 import ctypes
 
@@ -100,3 +105,86 @@ class GraphGenerator:
         flat = self.generated_likelihoods[self.generated_likelihoods != 0]        # :86-88
         graphs = (self.generated_nodes[:B], self.generated_edges[:B], self.generated_n_nodes[:B])
         return graphs, flat, final, self.properly_terminated[:B]
+
+
+class GraphGeneratorRL(GraphGenerator):
+    """RL rollout (reference `GraphGeneratorRL`): `sample(agent_model, prior_model)` returns the finished tensors,
+    `log(sum_t p_agent(a_t))` and `log(sum_t p_prior(a_t))` per molecule (GraphGeneratorRL.py:92-97) and the
+    properly-terminated flags; both log-likelihood vectors are differentiable w.r.t. the parameters of their model.
+
+    How the two differentiable likelihood streams ride on the one-stream round kernel: the kernel is given the slot
+    id (b + 1, exact in fp32) as the "likelihood" of every slot, so that after the rollout
+    `generated_likelihoods[g, t]` names the slot whose round-t action belongs to finished molecule g (0 = none).
+    The per-round sampled probabilities `softmax(logits_t)[b, a_t[b]]` are kept as autograd tensors and gathered
+    through that map -- the same values the reference scatters with in-place index assignments
+    (GraphGeneratorRL.py:325-326, 357-358, 409-424), without ~30 indexed autograd ops per round.
+    One K0 (bond lists + CSR) per round is shared by both models."""
+
+    def __init__(self, model, batch_size, **kw):
+        super().__init__(model, batch_size, **kw)
+        self.generated_agent_likelihoods = None
+        self.generated_prior_likelihoods = None
+
+    def build_graphs(self, agent_model=None, prior_model=None, replay=None, generator=None):
+        """replay: optional iterable of int32 [B] flat APD indices per round (instead of sampling from the agent).
+        Gradients are recorded if autograd is enabled and the models' parameters require them."""
+        agent = agent_model if agent_model is not None else self.model
+        prior = prior_model if prior_model is not None else self.model
+        B, N = self.batch_size, self.N
+        if B + 1 >= 1 << 24:
+            raise ValueError("batch_size must stay below 2**24 (slot ids travel as fp32)")
+        self._allocate()                                    # a fresh rollout (the reference builds a new generator)
+        tags = torch.arange(1, B + 1, dtype=torch.float32, device=self.device)
+        share = type(agent) is type(prior) and Fn.dims_key(agent, B) == Fn.dims_key(prior, B)
+        lik_a, lik_p = [], []
+        n_generated, rnd = 0, 0
+        replay = iter(replay) if replay is not None else None
+        st = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        while n_generated < B:
+            if rnd >= 2 * N:
+                raise RuntimeError("generation needs more than 2*max_n_nodes rounds: the per-slot likelihood buffer "
+                                   "(GraphGeneratorRL.py:175, 'the 2 is arbitrary') would overflow, as in the reference")
+            # the round kernel edits the batch in place while autograd keeps the inputs of every round: snapshot them
+            nodes_in, edges_in = self.nodes.clone(), self.edges.clone()
+            graph = Fn.build_graph(agent, edges_in)
+            out_a = agent(nodes_in, edges_in, graph=graph)                             # GraphGeneratorRL.py:131-132
+            out_p = prior(nodes_in, edges_in, graph=graph if share else None)
+            if replay is not None:
+                try:
+                    action = next(replay)
+                except StopIteration:
+                    raise RuntimeError("replay trace ended before batch_size molecules were finished") from None
+                action = action.to(self.device, torch.int32).contiguous()
+            else:
+                action, _ = Fn.sample_actions(out_a.detach(), generator=generator)
+            idx = action.long().unsqueeze(1)
+            lik_a.append(torch.softmax(out_a, dim=1).gather(1, idx).squeeze(1))       # `apds[apd_one_hot == 1]` :547-548
+            lik_p.append(torch.softmax(out_p, dim=1).gather(1, idx).squeeze(1))
+            check(lib.gib_generation_round(B, N, self.F, self.Ef, self.A, self.CH, rnd, _ptr(action), _ptr(tags),
+                                           _ptr(self.nodes), _ptr(self.edges), _ptr(self.n_nodes),
+                                           _ptr(self.likelihoods), _ptr(self.generated_nodes),
+                                           _ptr(self.generated_edges), _ptr(self.generated_n_nodes),
+                                           _ptr(self.generated_likelihoods), _ptr(self.properly_terminated),
+                                           self.capacity, _ptr(self._counters), _ptr(self._scratch), st),
+                  "gib_generation_round")
+            n_generated = int(self._counters[0].item())
+            rnd += 1
+        self.rounds = rnd
+        # (finished molecule, round) -> slot map written by the kernel; gather both likelihood streams through it
+        owner = self.generated_likelihoods[:, :rnd]                                     # [2B, rounds] slot id + 1
+        mask = (owner > 0).to(torch.float32)
+        slot = (owner.long() - 1).clamp_(min=0).t().contiguous()                        # [rounds, 2B]
+        pad = self.generated_likelihoods.shape[1] - rnd
+        for name, rounds_l in (("generated_agent_likelihoods", lik_a), ("generated_prior_likelihoods", lik_p)):
+            per_round = torch.stack(rounds_l)                                           # [rounds, B], differentiable
+            g = per_round.gather(1, slot).t() * mask                                    # [2B, rounds]
+            setattr(self, name, torch.nn.functional.pad(g, (0, pad)))                   # [2B, 2N] like the reference
+        return n_generated
+
+    def sample(self, agent_model, prior_model, generator=None, replay=None):
+        self.build_graphs(agent_model, prior_model, replay=replay, generator=generator)
+        B = self.batch_size
+        agent_ll = torch.log(torch.sum(self.generated_agent_likelihoods, dim=1)[:B])   # GraphGeneratorRL.py:92-94
+        prior_ll = torch.log(torch.sum(self.generated_prior_likelihoods, dim=1)[:B])   # :95-97
+        graphs = (self.generated_nodes[:B], self.generated_edges[:B], self.generated_n_nodes[:B])
+        return graphs, agent_ll, prior_ll, self.properly_terminated[:B]

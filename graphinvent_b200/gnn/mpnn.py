@@ -31,6 +31,7 @@ class _FusedMPNN(torch.nn.Module):
         self._packed = None
         self._packed_key = None
         self._grad_hook = None      # set by graphinvent_b200.parallel: called on the flat gradient bucket
+        self._graph_in = None       # transient: a shared GraphBatch handed to the next forward
         self.last_stats = {}
 
     # dims shared by every model; subclasses add their own fields
@@ -45,12 +46,14 @@ class _FusedMPNN(torch.nn.Module):
     def _dropout_ps(self):
         return [m.dropout_p for m in self.modules() if isinstance(m, MLP)]
 
-    def forward(self, nodes: torch.Tensor, edges: torch.Tensor) -> torch.Tensor:
+    def forward(self, nodes: torch.Tensor, edges: torch.Tensor, graph=None) -> torch.Tensor:
+        """`graph`: optional `functional.build_graph(model, edges)` shared between several models of one family
+        evaluated on the same batch (not part of the reference's signature)"""
         if self.training and any(p > 0.0 for p in self._dropout_ps()):
             # AlphaDropout draws from torch's RNG stream inside the reference's ATen graph; the
             # fused path cannot reproduce that stream (all reference defaults use p = 0).
             raise NotImplementedError("dropout_p > 0 in training mode is not supported by the fused sm_100a path")
-        return _F.mpnn_forward(self, nodes, edges)
+        return _F.mpnn_forward(self, nodes, edges, graph)
 
     def _gather_kwargs(self, node_features, hidden):
         C = self.constants

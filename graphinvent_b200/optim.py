@@ -41,10 +41,10 @@ class FlatAdam(torch.optim.Optimizer):
         if not ps:
             raise ValueError("FlatAdam: no parameters")
         dev = ps[0].device
+        _F._require_cuda(*ps)                  # raises: there is no CPU fallback
         for p in ps:
-            if p.device != dev or p.dtype != torch.float32 or not p.is_cuda:
-                raise RuntimeError("FlatAdam: all parameters must be float32 CUDA tensors on one device "
-                                   "(there is no CPU fallback)")
+            if p.device != dev or p.dtype != torch.float32:
+                raise RuntimeError("FlatAdam: all parameters must be float32 tensors on one CUDA device")
         self._off, o = [], 0
         for p in ps:
             self._off.append(o)

@@ -11,6 +11,10 @@ Parity pin: `tests/golden/generation_trace.npz` is a recording of the unmodified
 round + its final buffers, made by `tests/golden/make_generation_trace.py`); `tests/test_generation.py` replays the
 draws through this oracle and requires bit-exact buffers.  The CUDA kernels are then checked against this oracle on
 random action streams as well.
+
+RL twin (`GraphGeneratorRL.py:109-172, 227-438, 520-629`): the same state machine carrying TWO likelihood streams
+(agent = the sampling model, prior = the second model's probability of the same action); pass `rl=True` /
+`prior_likelihoods=`.  Pinned by `tests/golden/generation_rl_trace.npz` (`make_generation_rl_trace.py`).
 """
 import numpy as np
 
@@ -18,8 +22,9 @@ import numpy as np
 class GenerationState:
     """the tensors `GraphGenerator` keeps (initialize_graph_batch :387-423, allocate_graph_tensors :163-209)"""
 
-    def __init__(self, batch, N, A, CH, Ef):
+    def __init__(self, batch, N, A, CH, Ef, rl=False):
         self.B, self.N, self.A, self.CH, self.Ef, self.F = batch, N, A, CH, Ef, A + CH
+        self.rl = rl
         self.nodes = np.zeros((batch, N, self.F), np.float32)
         self.edges = np.zeros((batch, N, N, Ef), np.float32)
         self.n_nodes = np.zeros(batch, np.int32)
@@ -34,6 +39,9 @@ class GenerationState:
         self.generated_likelihoods = np.zeros((cap, 2 * N), np.float32)
         self.properly_terminated = np.zeros(cap, np.int8)
         self.n_generated = 0
+        if rl:                                  # GraphGeneratorRL.allocate_graph_tensors :200-217
+            self.prior_likelihoods = np.zeros((batch, 2 * N), np.float32)
+            self.generated_prior_likelihoods = np.zeros((cap, 2 * N), np.float32)
 
 
 def decode(state, b, a):
@@ -58,9 +66,12 @@ def decode(state, b, a):
     return 2, 0, 0, 0, 0, 0, False
 
 
-def generation_round(state, rnd, actions, likelihoods):
-    """one pass of the `while` body of build_graphs (:118-157); returns the number of graphs written this round"""
+def generation_round(state, rnd, actions, likelihoods, prior_likelihoods=None):
+    """one pass of the `while` body of build_graphs (:118-157; RL: GraphGeneratorRL.py:127-168); returns the number
+    of graphs written this round"""
     B, A = state.B, state.A
+    rl = prior_likelihoods is not None
+    assert rl == state.rl
     rec = [decode(state, b, int(actions[b])) for b in range(B)]
     term = [b for b in range(B) if rec[b][0] == 2]
     invalid = [b for b in range(B) if rec[b][6]]
@@ -70,12 +81,16 @@ def generation_round(state, rnd, actions, likelihoods):
     order = [b for b in term if b != 0] + [b for b in invalid if b != 0]          # :130-133
     for i, b in enumerate(order):                                                 # copy_terminated_graphs
         state.likelihoods[b, rnd] = likelihoods[b]
+        if rl:
+            state.prior_likelihoods[b, rnd] = prior_likelihoods[b]
         p = k + i
         if p < cap:
             state.generated_nodes[p] = state.nodes[b]
             state.generated_edges[p] = state.edges[b]
             state.generated_n_nodes[p] = state.n_nodes[b]
             state.generated_likelihoods[p] = state.likelihoods[b]
+            if rl:
+                state.generated_prior_likelihoods[p] = state.prior_likelihoods[b]
     state.n_generated = k + len(order)
     gone = set(order)
     for b in range(B):                                                            # apply_actions on every slot
@@ -89,16 +104,20 @@ def generation_round(state, rnd, actions, likelihoods):
                 state.edges[b, bt, bf, ty] = 1
                 state.edges[b, bf, bt, ty] = 1
             state.n_nodes[b] += 1
-            state.likelihoods[b, rnd] = likelihoods[b]
         elif kind == 1:
             state.edges[b, bf, bt, ty] = 1
             state.edges[b, bt, bf, ty] = 1
+        if kind in (0, 1):
             state.likelihoods[b, rnd] = likelihoods[b]
+            if rl:
+                state.prior_likelihoods[b, rnd] = prior_likelihoods[b]
     for b in order:                                                               # reset_graphs
         state.nodes[b] = 0
         state.edges[b] = 0
         state.n_nodes[b] = 0
         state.likelihoods[b] = 0
+        if rl:
+            state.prior_likelihoods[b] = 0
     state.nodes[0] = 1                                                            # dummy graph re-stamped (:462-465)
     state.edges[0, 0, 0, 0] = 1
     state.n_nodes[0] = 1

@@ -19,6 +19,65 @@ def test_cpu_parameters_fail_loudly():
         FlatAdam([torch.nn.Parameter(torch.zeros(4))], lr=-1.0)
 
 
+def test_flat_adam_host_logic_on_a_cpu_shim(monkeypatch):
+    """bucket layout, run detection (missing gradients, lagging step counts, scattered vs bucket gradients), lr /
+    betas pick-up, state_dict round trip and re-flattening after `.data` was re-assigned -- with the kernel played
+    by a numpy restatement (tests/hostshim.py); reference = torch.optim.Adam(foreach=False) on CPU"""
+    from tests import hostshim
+    from graphinvent_b200.optim import FlatAdam
+    launches = hostshim.install_optim_shims(monkeypatch)
+    gen = torch.Generator().manual_seed(5)
+    shapes = [(7, 5), (3,), (33, 17), (1,), (250, 100), (625,)]
+    init = _random_params(gen, shapes)
+    ref_p = [torch.nn.Parameter(t.clone()) for t in init]
+    our_p = [torch.nn.Parameter(t.clone()) for t in init]
+    ref = torch.optim.Adam(ref_p, lr=1e-3, weight_decay=0.01, foreach=False)
+    ours = FlatAdam(our_p, lr=1e-3, weight_decay=0.01)
+    assert ours._in_place() and [p.data_ptr() for p in our_p] == [ours._flat.data_ptr() + 4 * o for o in ours._off]
+    sched_r = torch.optim.lr_scheduler.OneCycleLR(ref, max_lr=1e-2, total_steps=12, pct_start=0.3)
+    sched_o = torch.optim.lr_scheduler.OneCycleLR(ours, max_lr=1e-2, total_steps=12, pct_start=0.3)
+
+    def close():
+        return max((a.detach() - b.detach()).abs().max().item() for a, b in zip(ref_p, our_p))
+
+    for step in range(5):                                        # scattered gradients, tensor 3 joins late
+        for i, (a, b, g) in enumerate(zip(ref_p, our_p, _random_params(gen, shapes))):
+            a.grad, b.grad = (None, None) if (i == 3 and step < 2) else (g.clone(), g.clone())
+        del launches[:]
+        ref.step(), ours.step(), sched_r.step(), sched_o.step()
+        assert ours.grad_copies_last_step == (5 if step < 2 else 6)
+        assert len(launches) == ours.launches_last_step == (2 if step < 2 else 3)
+        assert ref.param_groups[0]["lr"] == ours.param_groups[0]["lr"]
+        assert close() <= 1e-6, step
+    total = sum(t.numel() for t in init)
+    bucket = torch.randn(total, generator=gen)                   # the fused backward's layout: one flat bucket
+    o = 0
+    for a, b in zip(ref_p, our_p):
+        a.grad = bucket[o:o + a.numel()].view(a.shape).clone()
+        b.grad = bucket[o:o + a.numel()].view(a.shape)
+        o += a.numel()
+    del launches[:]
+    ref.step(), ours.step()
+    assert ours.grad_copies_last_step == 0 and launches == [7 * 5 + 3 + 33 * 17, 1, 250 * 100 + 625]
+    assert close() <= 1e-6
+    sd = copy.deepcopy(ours.state_dict())                        # same layout as torch.optim.Adam's
+    rsd = ref.state_dict()
+    assert sd["param_groups"][0]["params"] == rsd["param_groups"][0]["params"]
+    for k in rsd["state"]:
+        assert float(rsd["state"][k]["step"]) == float(sd["state"][k]["step"])
+        assert (rsd["state"][k]["exp_avg_sq"] - sd["state"][k]["exp_avg_sq"]).abs().max().item() <= 1e-7
+    for p in our_p:                                              # e.g. model.to(...) re-assigned the storage
+        p.data = p.data.clone()
+    assert not ours._in_place()
+    for a, b, g in zip(ref_p, our_p, _random_params(gen, shapes)):
+        a.grad, b.grad = g.clone(), g.clone()
+    ref.step(), ours.step()
+    assert ours._in_place() and close() <= 1e-6                   # re-flattened, moments and step counts kept
+    again = FlatAdam(our_p, lr=1e-3, weight_decay=0.01)
+    again.load_state_dict(sd)
+    assert again._steps == [int(sd["state"][k]["step"]) for k in range(len(our_p))]
+
+
 def _random_params(gen, shapes):
     return [torch.randn(*s, generator=gen) for s in shapes]
 
