@@ -35,6 +35,7 @@ _PROTOS = {
     "gib_set_tensor_cores": (None, [c_i]),
     "gib_get_tensor_cores": (c_i, []),
     "gib_tc_debug": (None, [c_i]),
+    "gib_tc_timing": (None, [c_p]),
     "gib_graph_count_ws_bytes": (c_sz, [c_p]),
     "gib_graph_count": (c_i, [c_p, c_p, c_p, c_p]),
     "gib_graph_bytes": (c_sz, [c_p, c_p]),

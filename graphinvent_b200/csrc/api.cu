@@ -114,6 +114,7 @@ int gib_version(void) { return 101; }
 void gib_set_tensor_cores(int on) { g_use_tc = on != 0; }
 int gib_get_tensor_cores(void) { return g_use_tc ? 1 : 0; }
 void gib_tc_debug(int mode) { g_tc_debug = mode; }
+void gib_tc_timing(long long* device_buf) { g_tc_timing = device_buf; }
 
 static int groups_of(const gib_dims* d) { return d->model == GIB_EMN ? 1 : d->Ef; }
 

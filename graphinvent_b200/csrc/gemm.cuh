@@ -60,6 +60,7 @@ int gemm_nt_group(const GemmNT* ps, int n, cudaStream_t st);      // dispatcher:
 bool tc_eligible(const GemmNT& p);
 extern bool g_use_tc;
 extern int g_tc_debug;
+extern long long* g_tc_timing;
 int gemm_dw(const GemmDW& q, cudaStream_t st);
 void gemm_dw_plan(int M, int Nn, int Kk, int* splits, int* chunk);
 void tc_dw_plan(int M, int Nn, int Kk, int* splits, int* chunk);

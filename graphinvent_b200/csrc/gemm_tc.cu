@@ -64,6 +64,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (clock64() - t0 > 20000000000LL) __trap();   // ~10 s: a dead-lock, not contention
 }
 
+// mbar_wait that also accumulates the cycles spent waiting (TIMING instantiation)
+template <bool TIMING>
+__device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, long long& acc) {
+  if constexpr (TIMING) {
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    acc += clock64() - t0;
+  } else {
+    mbar_wait(bar, parity);
+  }
+}
+
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -174,7 +186,21 @@ struct Params {
   // activations themselves (MN-major for the MMA), problem 0 only, g[0].C = split-K workspace
   int tn, splits, chunk_rows, tn_rows, tn_nn, tn_kk;
   int debug;   // bit0: skip the hi/lo split (timing experiments only), bit1: skip the epilogue stores
+  // TIMING instantiation only: [2 (NT, TN)][TIMING_CTAS][TIMING_SLOTS] clock64 totals per role, ACCUMULATED over
+  // launches (each CTA index owns its row; tcgen05 launches are stream-ordered)
+  long long* timing;
 };
+
+// where a CTA's cycles go, per role (one representative thread each); filled by tc_gemm_nt_kernel<SPLIT, true>
+enum tc_timing_slots {
+  TS_TMA_WAIT_EMPTY = 0, TS_TMA_TOTAL, TS_MMA_WAIT_SPLIT, TS_MMA_WAIT_ACC, TS_MMA_TOTAL, TS_SPL_WAIT_RAW, TS_SPL_WORK,
+  TS_SPL_TOTAL, TS_EPI_WAIT_ACC, TS_EPI_WORK, TS_EPI_TOTAL, TS_KERNEL_TOTAL, TS_ITEMS, TS_KBLOCKS, TS_LAUNCHES,
+  TIMING_SLOTS = 16, TIMING_CTAS = 160
+};
+
+__device__ __forceinline__ long long* timing_row(const Params& P) {
+  return P.timing + ((size_t)(P.tn ? TIMING_CTAS : 0) + blockIdx.x) * TIMING_SLOTS;
+}
 
 struct Item { int p, m0, n0, nkb, z; };
 
@@ -198,7 +224,10 @@ __device__ __forceinline__ Item decode_item(const Params& P, int item) {
   return it;
 }
 
-template <int SPLIT>   // 0: hi = truncation, lo = exact remainder;  1: hi, lo both round-to-nearest (cvt.rna)
+// SPLIT 0: hi = truncation, lo = exact remainder;  1: hi, lo both round-to-nearest (cvt.rna);
+//       2: hi = the raw value (the MMA reads its top 19 bits = truncation, nothing is written back), lo = rna(x - trunc(x))
+// TIMING: accumulate per-role wait / work cycles into P.timing (diagnosis builds; the product uses <1, false>)
+template <int SPLIT, bool TIMING = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_gemm_nt_kernel(const __grid_constant__ Maps maps, const Params P) {
   extern __shared__ uint8_t smem_raw[];
@@ -212,6 +241,8 @@ tc_gemm_nt_kernel(const __grid_constant__ Maps maps, const Params P) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  long long t_kernel0 = 0;
+  if constexpr (TIMING) t_kernel0 = clock64();
   // work items: NT = output tiles of all problems; TN = (output tile, reduction chunk) pairs
   const int num_tiles = P.tn ? P.m_tiles[0] * P.n_tiles[0] * P.splits : P.tile_begin[P.nprob];
 
@@ -242,6 +273,8 @@ tc_gemm_nt_kernel(const __grid_constant__ Maps maps, const Params P) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      long long t_wait = 0, t_begin = 0;
+      if constexpr (TIMING) t_begin = clock64();
       for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
         const Item w = decode_item(P, item);
         const CUtensorMap* map_a = &maps.a[w.p];
@@ -249,7 +282,7 @@ tc_gemm_nt_kernel(const __grid_constant__ Maps maps, const Params P) {
         const int m0 = w.m0, n0 = w.n0, nkb = w.nkb;
         const int r0 = w.z * P.chunk_rows;
         for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_wait_t<TIMING>(&empty[stage], phase ^ 1, t_wait);
           uint8_t* st = smem + stage * STAGE_BYTES;
           const bool presplit = !P.tn && P.bsplit[w.p];
           mbar_arrive_expect_tx(&full_raw[stage], (presplit ? 3 : 2) * TILE_BYTES);
@@ -268,6 +301,11 @@ tc_gemm_nt_kernel(const __grid_constant__ Maps maps, const Params P) {
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
+      if constexpr (TIMING) {
+        long long* T = timing_row(P);
+        T[TS_TMA_WAIT_EMPTY] += t_wait;
+        T[TS_TMA_TOTAL] += clock64() - t_begin;
+      }
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
@@ -275,11 +313,14 @@ tc_gemm_nt_kernel(const __grid_constant__ Maps maps, const Params P) {
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      long long t_wait_split = 0, t_wait_acc = 0, t_begin = 0, n_kb = 0;
+      if constexpr (TIMING) t_begin = clock64();
       for (int item = blockIdx.x; item < num_tiles; item += gridDim.x, ++it) {
         const int nkb = decode_item(P, item).nkb;
+        if constexpr (TIMING) n_kb += nkb;
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+        mbar_wait_t<TIMING>(&acc_empty[acc], acc_phase ^ 1, t_wait_acc);
         tc_fence_after();
         // Two accumulators per tile.  The tensor core adds into TMEM with truncation, one rounding per MMA; the
         // hi*lo / lo*hi products are 2^-11 of the hi*hi ones, so giving them their own accumulator keeps their
@@ -288,7 +329,7 @@ tc_gemm_nt_kernel(const __grid_constant__ Maps maps, const Params P) {
         const uint32_t tmem_x = tmem_d + BN;                     // sum of hi*lo + lo*hi
         const uint32_t idesc = P.tn ? IDESC_TN : IDESC;
         for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(&full_split[stage], phase);
+          mbar_wait_t<TIMING>(&full_split[stage], phase, t_wait_split);
           tc_fence_after();
           const uint32_t a_hi = smem_u32(smem + stage * STAGE_BYTES);
           uint64_t d_ahi, d_alo, d_bhi, d_blo, kstep;
@@ -315,18 +356,30 @@ tc_gemm_nt_kernel(const __grid_constant__ Maps maps, const Params P) {
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
+      if constexpr (TIMING) {
+        long long* T = timing_row(P);
+        T[TS_MMA_WAIT_SPLIT] += t_wait_split;
+        T[TS_MMA_WAIT_ACC] += t_wait_acc;
+        T[TS_MMA_TOTAL] += clock64() - t_begin;
+        T[TS_ITEMS] += it;
+        T[TS_KBLOCKS] += n_kb;
+      }
     }
   } else if (warp < 6) {
     // ================= splitters: raw fp32 -> (hi, lo) TF32 pairs, in place =================
     const int t = threadIdx.x - 64;  // 0..127
     int stage = 0;
     uint32_t phase = 0;
+    long long t_wait = 0, t_work = 0, t_begin = 0;
+    if constexpr (TIMING) t_begin = clock64();
     for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
       const Item wi = decode_item(P, item);
       const int nkb = wi.nkb;
       const int nops = (!P.tn && P.bsplit[wi.p]) ? 1 : 2;   // pre-split weights: only the A tile needs splitting
       for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(&full_raw[stage], phase);
+        mbar_wait_t<TIMING>(&full_raw[stage], phase, t_wait);
+        long long t_w0 = 0;
+        if constexpr (TIMING) t_w0 = clock64();
         uint8_t* st = smem + stage * STAGE_BYTES;
         if (!(P.debug & 1)) {
           auto split_tile = [&](int op) {
@@ -337,7 +390,12 @@ tc_gemm_nt_kernel(const __grid_constant__ Maps maps, const Params P) {
               const int c = t + i * 128;
               const float4 v = hi[c];
               float4 h, l;
-              if (SPLIT == 1) {    // round-to-nearest split: 3 conversions per element, smallest error
+              if (SPLIT == 2) {    // hi stays the raw tile (not written back); only the rounded remainder is stored
+                l.x = __uint_as_float(to_tf32(v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u)));
+                l.y = __uint_as_float(to_tf32(v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u)));
+                l.z = __uint_as_float(to_tf32(v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u)));
+                l.w = __uint_as_float(to_tf32(v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u)));
+              } else if (SPLIT == 1) {    // round-to-nearest split: 3 conversions per element, smallest error
                 h.x = __uint_as_float(to_tf32(v.x)); l.x = __uint_as_float(to_tf32(v.x - h.x));
                 h.y = __uint_as_float(to_tf32(v.y)); l.y = __uint_as_float(to_tf32(v.y - h.y));
                 h.z = __uint_as_float(to_tf32(v.z)); l.z = __uint_as_float(to_tf32(v.z - h.z));
@@ -348,7 +406,7 @@ tc_gemm_nt_kernel(const __grid_constant__ Maps maps, const Params P) {
                 h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
                 h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
               }
-              hi[c] = h;
+              if (SPLIT != 2) hi[c] = h;
               lo[c] = l;
             }
           };
@@ -357,7 +415,16 @@ tc_gemm_nt_kernel(const __grid_constant__ Maps maps, const Params P) {
         }
         fence_proxy_async();           // generic-proxy smem writes -> visible to the tensor-core (async) proxy
         mbar_arrive(&full_split[stage]);
+        if constexpr (TIMING) t_work += clock64() - t_w0;
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+    if constexpr (TIMING) {
+      if (t == 0) {
+        long long* T = timing_row(P);
+        T[TS_SPL_WAIT_RAW] += t_wait;
+        T[TS_SPL_WORK] += t_work;
+        T[TS_SPL_TOTAL] += clock64() - t_begin;
       }
     }
   } else {
@@ -371,6 +438,8 @@ tc_gemm_nt_kernel(const __grid_constant__ Maps maps, const Params P) {
     float* stg = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256) + (warp - 6) * (32 * EPI_LD);
     const int rr = lane >> 2, cc = (lane & 3) * 4;
     int it = 0;
+    long long t_wait = 0, t_work = 0, t_begin = 0;
+    if constexpr (TIMING) t_begin = clock64();
     for (int item = blockIdx.x; item < num_tiles; item += gridDim.x, ++it) {
       const Item w = decode_item(P, item);
       const GemmNT& g = P.g[w.p];
@@ -380,7 +449,9 @@ tc_gemm_nt_kernel(const __grid_constant__ Maps maps, const Params P) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int m0 = w.m0, n0 = w.n0;
-      mbar_wait(&acc_full[acc], acc_phase);
+      mbar_wait_t<TIMING>(&acc_full[acc], acc_phase, t_wait);
+      long long t_w0 = 0;
+      if constexpr (TIMING) t_w0 = clock64();
       tc_fence_after();
 #pragma unroll 1
       for (int chunk = 0; chunk < 4; ++chunk) {
@@ -445,11 +516,27 @@ tc_gemm_nt_kernel(const __grid_constant__ Maps maps, const Params P) {
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[acc]);
+      if constexpr (TIMING) t_work += clock64() - t_w0;
+    }
+    if constexpr (TIMING) {
+      if (warp == 6 && lane == 0) {
+        long long* T = timing_row(P);
+        T[TS_EPI_WAIT_ACC] += t_wait;
+        T[TS_EPI_WORK] += t_work;
+        T[TS_EPI_TOTAL] += clock64() - t_begin;
+      }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (TIMING) {
+    if (threadIdx.x == 0) {
+      long long* T = timing_row(P);
+      T[TS_KERNEL_TOTAL] += clock64() - t_kernel0;
+      T[TS_LAUNCHES] += 1;
+    }
+  }
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
@@ -492,7 +579,8 @@ static int make_map(CUtensorMap* map, const float* base, int rows, int cols, int
 }  // namespace tc
 
 bool g_use_tc = true;
-int g_tc_debug = 0;
+int g_tc_debug = 0;               // bit 2 (4): truncation split, bit 4 (16): ignore pre-split weights, bit 6 (64): SPLIT = 2
+long long* g_tc_timing = nullptr; // non-null: launch the TIMING instantiation, per-CTA role timings land here
 
 bool tc_eligible(const GemmNT& p) {
   return p.M >= 1 && p.N >= 1 && p.K >= 16 && (p.K % 16) == 0 && (p.lda % 4) == 0 && (p.ldb % 4) == 0 &&
@@ -509,10 +597,30 @@ static int tc_prepare(int* num_sms_out) {
     GIB_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     GIB_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_nt_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     GIB_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_nt_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    GIB_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_nt_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    GIB_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_nt_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    GIB_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_nt_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_done = true;
   }
   *num_sms_out = num_sms;
   return 0;
+}
+
+// product: <1> (round-to-nearest split).  Diagnosis builds behind g_tc_debug / g_tc_timing (gib_tc_debug, gib_tc_timing).
+static void launch_tc(int grid, const tc::Maps& maps, tc::Params& P, cudaStream_t st) {
+  using namespace tc;
+  P.timing = g_tc_timing;
+  const bool split2 = (g_tc_debug & 64) != 0;
+  if (P.timing) {
+    if (split2) tc_gemm_nt_kernel<2, true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps, P);
+    else tc_gemm_nt_kernel<1, true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps, P);
+  } else if (g_tc_debug & 4) {
+    tc_gemm_nt_kernel<0><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps, P);
+  } else if (split2) {
+    tc_gemm_nt_kernel<2><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps, P);
+  } else {
+    tc_gemm_nt_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps, P);
+  }
 }
 
 // up to MAXP independent NT problems in one persistent launch
@@ -551,9 +659,7 @@ int gemm_nt_tc_group(const GemmNT* ps, int n, cudaStream_t st) {
   P.debug = g_tc_debug;
   const int grid = tiles < num_sms ? tiles : num_sms;
   ProfScope prof(PROF_GEMM_NT, work, st);
-  // default: round-to-nearest split (same speed -- the splitters are smem-bound -- and ~30% smaller error)
-  if (g_tc_debug & 4) tc_gemm_nt_kernel<0><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps, P);
-  else tc_gemm_nt_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps, P);
+  launch_tc(grid, maps, P, st);
   GIB_LAUNCH_CHECK();
   return 0;
 }
@@ -600,8 +706,7 @@ int gemm_dw_tc_partials(const GemmDW& q, int* splits_out, cudaStream_t st) {
   P.debug = g_tc_debug;
   const int items = P.m_tiles[0] * P.n_tiles[0] * splits;
   const int grid = items < num_sms ? items : num_sms;
-  if (g_tc_debug & 4) tc_gemm_nt_kernel<0><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps, P);
-  else tc_gemm_nt_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps, P);
+  launch_tc(grid, maps, P, st);
   GIB_LAUNCH_CHECK();
   *splits_out = splits;
   return 0;

@@ -70,8 +70,18 @@ int gib_version(void);
 /* tcgen05 3xTF32 GEMM path on (default) / off (fp32 SIMT GEMMs only); process-wide switch */
 void gib_set_tensor_cores(int on);
 int gib_get_tensor_cores(void);
-/* timing experiments only (results become wrong): bit0 skip the hi/lo split, bit1 skip epilogue stores */
+/* diagnosis switches of the tcgen05 GEMM (process-wide, default 0).  Results stay correct with bit2 (truncation
+ * split), bit4 (split the weights in the kernel instead of using the packed hi/lo planes) and bit6 (hi operand = raw
+ * tile, only the rounded remainder is written); bit0 (skip the split) and bit1 (skip epilogue stores) are timing
+ * experiments whose results are wrong. */
 void gib_tc_debug(int mode);
+/* device_buf != NULL: every following tcgen05 GEMM launch runs its TIMING build and ADDS clock64 totals per role
+ * into device_buf[mode][cta][16] (int64; mode 0 = forward/dX launches, 1 = weight-gradient launches; 160 CTA rows
+ * per mode, i.e. 2 * 160 * 16 * 8 bytes, zeroed by the caller): 0 TMA wait-for-free-stage, 1 TMA loop, 2 MMA
+ * wait-for-split-stage, 3 MMA wait-for-free-accumulator, 4 MMA loop, 5 splitter wait-for-TMA, 6 splitter work,
+ * 7 splitter loop, 8 epilogue wait-for-accumulator, 9 epilogue work, 10 epilogue loop, 11 whole kernel, 12 work
+ * items, 13 k-blocks, 14 launches.  NULL switches back to the product build. */
+void gib_tc_timing(long long* device_buf);
 
 /* ---- K0: edges -> bond entries + CSR.  Replaces summation_mpnn.py:102-118,
  *      aggregation_mpnn.py:105-148, edge_mpnn.py:104-173. ------------------------------- */
