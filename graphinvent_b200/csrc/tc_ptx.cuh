@@ -1,0 +1,128 @@
+// PTX wrappers shared by the tcgen05 GEMM kernels (gemm_tc.cu, gemm_tc2.cu): mbarrier, TMA, tcgen05.mma / commit /
+// ld, fences, UMMA shared-memory descriptors, the TF32 conversion and the fast epilogue activation.  sm_100a only.
+#pragma once
+#include <cuda.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace gib {
+namespace tcptx {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: ~10 s of wall clock, then trap (surfaces as a CUDA error instead of hanging the box)
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity))
+    if (clock64() - t0 > 20000000000LL) __trap();   // ~10 s: a dead-lock, not contention
+}
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      :
+      : "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile (rows x 32 fp32): 8-row groups are 1024 B apart (SBO), descriptor
+// version 1 (sm_100), layout type 2 = SWIZZLE_128B.  (cute/arch/mma_sm100_desc.hpp: SmemDescriptor)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);   // start address [0,14)
+  d |= (uint64_t)1 << 16;                        // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset [32,46)
+  d |= (uint64_t)1 << 46;                        // descriptor version [46,48)
+  d |= (uint64_t)2 << 61;                        // SWIZZLE_128B [61,64)
+  return d;
+}
+// MN-major operand tile as TMA lays down four [32 rows x 32 floats] boxes back to back.  For MN-major 32-bit
+// operands the only UMMA layout is SWIZZLE_128B_BASE32B (layout type 1, Swizzle<2,5,2>: 32-byte chunks XOR-ed with
+// the row index mod 4, 4-row atoms; cutlass sm100_common.inl:92) = TMA's CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+// Along MN 32 floats are contiguous (one 128 B row), the next 32-float column group starts 4096 B later (LBO),
+// reduction rows are 128 B apart and 4-row atoms 512 B apart (SBO).  One tf32 MMA consumes 8 rows = 1024 B.
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(4096 >> 4) << 16;              // leading byte offset: next column group
+  d |= (uint64_t)(512 >> 4) << 32;               // stride byte offset: next 4-row atom
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;                        // SWIZZLE_128B_BASE32B
+  return d;
+}
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+
+// epilogue activation: SELU through the hardware exp2 path (MUFU), |abs err| <~ 2e-7 -- the four epilogue warps
+// must stay under the MMA time per tile, and expm1f's ~30-instruction software path does not
+__device__ __forceinline__ float act_fast(float x, int act) {
+  if (act == ACT_SELU) return x > 0.f ? GIB_SELU_SCALE * x : (GIB_SELU_SCALE * GIB_SELU_ALPHA) * (__expf(x) - 1.f);
+  if (act == ACT_TANH) return tanhf(x);
+  return x;
+}
+
+}  // namespace tcptx
+}  // namespace gib
