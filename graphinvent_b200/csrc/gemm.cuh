@@ -58,6 +58,11 @@ int gemm_nt_tc(const GemmNT& p, cudaStream_t st);
 int gemm_nt_tc_group(const GemmNT* ps, int n, cudaStream_t st);   // n <= 4 independent problems, one launch
 int gemm_nt_group(const GemmNT* ps, int n, cudaStream_t st);      // dispatcher: grouped tcgen05 launch or per-problem
 bool tc_eligible(const GemmNT& p);
+// CTA-pair candidate (gemm_tc2.cu; gib_tc_debug bit 7): NT problems whose weights come as pre-split hi / lo planes
+bool tc2_eligible(const GemmNT& p);
+int gemm_nt_tc2_group(const GemmNT* ps, int n, cudaStream_t st);
+// 2-D fp32 TMA descriptor (CUtensorMap*) with a [box_rows x 32 floats] box, 128-byte swizzle
+int tc_make_map(void* cu_tensor_map, const float* base, int rows, int cols, int ld, int box_rows);
 extern bool g_use_tc;
 extern int g_tc_debug;
 extern long long* g_tc_timing;

@@ -466,8 +466,13 @@ static int make_map(CUtensorMap* map, const float* base, int rows, int cols, int
 
 }  // namespace tc
 
+int tc_make_map(void* map, const float* base, int rows, int cols, int ld, int box_rows) {
+  return tc::make_map(reinterpret_cast<CUtensorMap*>(map), base, rows, cols, ld, box_rows);
+}
+
 bool g_use_tc = true;
-int g_tc_debug = 0;               // bit 2 (4): truncation split, bit 4 (16): ignore pre-split weights, bit 6 (64): SPLIT = 2
+int g_tc_debug = 0;               // bit 2 (4): truncation split, bit 4 (16): ignore pre-split weights, bit 6 (64): SPLIT = 2,
+                                  // bit 7 (128): CTA-pair kernel (gemm_tc2.cu) for problems with pre-split weights
 long long* g_tc_timing = nullptr; // non-null: launch the TIMING instantiation, per-CTA role timings land here
 
 bool tc_eligible(const GemmNT& p) {
@@ -515,6 +520,12 @@ static void launch_tc(int grid, const tc::Maps& maps, tc::Params& P, cudaStream_
 int gemm_nt_tc_group(const GemmNT* ps, int n, cudaStream_t st) {
   using namespace tc;
   if (n < 1 || n > MAXP) { set_error("gemm_nt_tc_group: %d problems (max %d)", n, MAXP); return -2; }
+  if (g_tc_debug & 128) {           // candidate CTA-pair kernel: whole group or nothing
+    bool all = true;
+    for (int i = 0; i < n; ++i)
+      if (ps[i].M > 0 && ps[i].N > 0 && !tc2_eligible(ps[i])) all = false;
+    if (all) return gemm_nt_tc2_group(ps, n, st);
+  }
   int num_sms = 0;
   GIB_TRY(tc_prepare(&num_sms));
   Maps maps;
