@@ -61,8 +61,10 @@ bool tc_eligible(const GemmNT& p);
 // CTA-pair candidate (gemm_tc2.cu; gib_tc_debug bit 7): NT problems whose weights come as pre-split hi / lo planes
 bool tc2_eligible(const GemmNT& p);
 int gemm_nt_tc2_group(const GemmNT* ps, int n, cudaStream_t st);
-// 2-D fp32 TMA descriptor (CUtensorMap*) with a [box_rows x 32 floats] box, 128-byte swizzle
-int tc_make_map(void* cu_tensor_map, const float* base, int rows, int cols, int ld, int box_rows);
+int gemm_dw_tc2_partials(const GemmDW& q, int* splits_out, cudaStream_t st);   // same contract as gemm_dw_tc_partials
+// 2-D fp32 TMA descriptor (CUtensorMap*) with a [box_rows x 32 floats] box; 128-byte swizzle for K-major operand
+// tiles, its 32-byte-atom variant for MN-major ones (weight-gradient mode)
+int tc_make_map(void* cu_tensor_map, const float* base, int rows, int cols, int ld, int box_rows, int mn_major);
 extern bool g_use_tc;
 extern int g_tc_debug;
 extern long long* g_tc_timing;

@@ -466,8 +466,9 @@ static int make_map(CUtensorMap* map, const float* base, int rows, int cols, int
 
 }  // namespace tc
 
-int tc_make_map(void* map, const float* base, int rows, int cols, int ld, int box_rows) {
-  return tc::make_map(reinterpret_cast<CUtensorMap*>(map), base, rows, cols, ld, box_rows);
+int tc_make_map(void* map, const float* base, int rows, int cols, int ld, int box_rows, int mn_major) {
+  return tc::make_map(reinterpret_cast<CUtensorMap*>(map), base, rows, cols, ld, box_rows,
+                      mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 bool g_use_tc = true;
@@ -585,6 +586,7 @@ bool tc_dw_eligible(const GemmDW& q) {
 // partial products into q.scratch ([splits][Nn][Kk]); the caller reduces them (reduce_grads_kernel)
 int gemm_dw_tc_partials(const GemmDW& q, int* splits_out, cudaStream_t st) {
   using namespace tc;
+  if (g_tc_debug & 128) return gemm_dw_tc2_partials(q, splits_out, st);   // candidate CTA-pair kernel
   int num_sms = 0;
   GIB_TRY(tc_prepare(&num_sms));
   int splits, chunk;

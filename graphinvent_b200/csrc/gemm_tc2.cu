@@ -18,6 +18,9 @@
 // Cross-CTA hand-offs:  splitters -> leader's full_split (remote mbarrier.arrive, one per warp);
 //                       tcgen05.commit.cta_group::2 multicast -> both CTAs' empty[stage] / acc_full[acc];
 //                       epilogue warps -> leader's acc_empty (remote arrive).
+// Weight-gradient (TN) mode as in gemm_tc.cu: P[z][n][k] = sum_{m in chunk z} G[m,n] X[m,k]; the activations are the
+// MN-major operands themselves, the pair covers 256 columns of G x 128 columns of X (each CTA: 128 / 64), both
+// operands are split in the kernel (raw tile = hi, written: lo).
 // Every wait is bounded (trap, never a hang).
 #include <cuda.h>
 #include <string.h>
@@ -51,6 +54,7 @@ static_assert(SMEM_BYTES <= 232448, "dynamic shared memory budget of sm_100a");
 
 // instruction descriptor as in gemm_tc.cu, M = 256 (the pair), N = 128, both operands K-major
 constexpr uint32_t IDESC2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+constexpr uint32_t IDESC2_TN = IDESC2 | (1u << 15) | (1u << 16);   // A and B MN-major
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -91,9 +95,9 @@ __device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {
 }
 
 struct Maps {
-  CUtensorMap a[MAXP];      // raw fp32 activations, box 128 rows x 32 floats
-  CUtensorMap b_hi[MAXP];   // TF32 hi plane of the packed weights, box 64 rows x 32 floats
-  CUtensorMap b_lo[MAXP];   // lo plane
+  CUtensorMap a[MAXP];      // NT: raw fp32 activations, box 128 rows x 32 floats.  TN: G, box 32 rows x 32 floats
+  CUtensorMap b_hi[MAXP];   // NT: TF32 hi plane of the packed weights, box 64 rows x 32 floats.  TN: X, box 32 x 32
+  CUtensorMap b_lo[MAXP];   // NT: lo plane
 };
 
 struct Params {
@@ -101,16 +105,29 @@ struct Params {
   int m_pairs[MAXP], n_tiles[MAXP], k_blocks[MAXP], item_begin[MAXP + 1];
   int nprob;
   int debug;
+  // TN (weight-gradient) mode: problem 0 only; g[0].C = split-K workspace [splits][tn_nn][tn_kk]
+  int tn, splits, chunk_rows, tn_rows, tn_nn, tn_kk;
 };
 
-struct Item { int p, m0, n0, nkb; };   // m0 = first row of the PAIR's 256-row tile
+struct Item { int p, m0, n0, nkb, z; };   // m0 = first row of the PAIR's 256-row tile
 
 __device__ __forceinline__ Item decode_item(const Params& P, int item) {
+  if (P.tn) {
+    const int tiles = P.m_pairs[0] * P.n_tiles[0];
+    const int t = item % tiles;
+    Item it;
+    it.p = 0; it.z = item / tiles;
+    it.m0 = (t / P.n_tiles[0]) * (2 * BM);
+    it.n0 = (t % P.n_tiles[0]) * BN;
+    const int r0 = it.z * P.chunk_rows;
+    it.nkb = ceil_div(min(P.tn_rows, r0 + P.chunk_rows) - r0, BKF);
+    return it;
+  }
   int p = 0;
   while (p + 1 < P.nprob && item >= P.item_begin[p + 1]) ++p;
   const int t = item - P.item_begin[p];
   Item it;
-  it.p = p;
+  it.p = p; it.z = 0;
   it.m0 = (t / P.n_tiles[p]) * (2 * BM);
   it.n0 = (t % P.n_tiles[p]) * BN;
   it.nkb = P.k_blocks[p];
@@ -134,7 +151,7 @@ tc2_gemm_nt_kernel(const __grid_constant__ Maps maps, const Params P) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();         // 0 = leader (issues the MMAs), 1 = peer
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
-  const int num_items = P.item_begin[P.nprob];
+  const int num_items = P.tn ? P.m_pairs[0] * P.n_tiles[0] * P.splits : P.item_begin[P.nprob];
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -171,10 +188,21 @@ tc2_gemm_nt_kernel(const __grid_constant__ Maps maps, const Params P) {
         for (int kb = 0; kb < w.nkb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* st = smem + stage * STAGE_BYTES;
-          mbar_arrive_expect_tx(&full_raw[stage], A_BYTES + 2 * BH_BYTES);
-          tma_load_2d(&maps.a[w.p], &full_raw[stage], st, kb * BKF, m0);
-          tma_load_2d(&maps.b_hi[w.p], &full_raw[stage], st + 2 * A_BYTES, kb * BKF, nb0);
-          tma_load_2d(&maps.b_lo[w.p], &full_raw[stage], st + 2 * A_BYTES + BH_BYTES, kb * BKF, nb0);
+          if (!P.tn) {
+            mbar_arrive_expect_tx(&full_raw[stage], A_BYTES + 2 * BH_BYTES);
+            tma_load_2d(&maps.a[w.p], &full_raw[stage], st, kb * BKF, m0);
+            tma_load_2d(&maps.b_hi[w.p], &full_raw[stage], st + 2 * A_BYTES, kb * BKF, nb0);
+            tma_load_2d(&maps.b_lo[w.p], &full_raw[stage], st + 2 * A_BYTES + BH_BYTES, kb * BKF, nb0);
+          } else {
+            mbar_arrive_expect_tx(&full_raw[stage], A_BYTES + BH_BYTES);
+            const int row = w.z * P.chunk_rows + kb * BKF;      // 32 reduction rows per stage
+#pragma unroll
+            for (int j = 0; j < 4; ++j)                         // four 32-float column groups of G
+              tma_load_2d(&maps.a[0], &full_raw[stage], st + j * 4096, m0 + 32 * j, row);
+#pragma unroll
+            for (int j = 0; j < 2; ++j)                         // two column groups of X (this CTA's half)
+              tma_load_2d(&maps.b_hi[0], &full_raw[stage], st + 2 * A_BYTES + j * 4096, nb0 + 32 * j, row);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -197,16 +225,24 @@ tc2_gemm_nt_kernel(const __grid_constant__ Maps maps, const Params P) {
           mbar_wait(&full_split[stage], phase);
           tc_fence_after();
           const uint32_t base = smem_u32(smem + stage * STAGE_BYTES);
-          const uint64_t d_ahi = make_desc(base), d_alo = make_desc(base + A_BYTES);
-          const uint64_t d_bhi = make_desc(base + 2 * A_BYTES), d_blo = make_desc(base + 2 * A_BYTES + BH_BYTES);
-          constexpr uint64_t kstep = 32 >> 4;    // 8 tf32 = 32 B along K, in 16-byte units
+          uint64_t d_ahi, d_alo, d_bhi, d_blo, kstep;
+          if (!P.tn) {
+            d_ahi = make_desc(base); d_alo = make_desc(base + A_BYTES);
+            d_bhi = make_desc(base + 2 * A_BYTES); d_blo = make_desc(base + 2 * A_BYTES + BH_BYTES);
+            kstep = 32 >> 4;       // 8 tf32 = 32 B along K, in 16-byte units
+          } else {
+            d_ahi = make_desc_mn(base); d_alo = make_desc_mn(base + A_BYTES);
+            d_bhi = make_desc_mn(base + 2 * A_BYTES); d_blo = make_desc_mn(base + 2 * A_BYTES + BH_BYTES);
+            kstep = 1024 >> 4;     // 8 reduction rows = one 1024-byte swizzle atom
+          }
+          const uint32_t idesc = P.tn ? IDESC2_TN : IDESC2;
 #pragma unroll
           for (int k = 0; k < BKF / 8; ++k)
-            umma2_tf32(tmem_d, d_ahi + k * kstep, d_bhi + k * kstep, IDESC2, (kb | k) != 0);
+            umma2_tf32(tmem_d, d_ahi + k * kstep, d_bhi + k * kstep, idesc, (kb | k) != 0);
 #pragma unroll
           for (int k = 0; k < BKF / 8; ++k) {
-            umma2_tf32(tmem_x, d_alo + k * kstep, d_bhi + k * kstep, IDESC2, (kb | k) != 0);
-            umma2_tf32(tmem_x, d_ahi + k * kstep, d_blo + k * kstep, IDESC2, 1);
+            umma2_tf32(tmem_x, d_alo + k * kstep, d_bhi + k * kstep, idesc, (kb | k) != 0);
+            umma2_tf32(tmem_x, d_ahi + k * kstep, d_blo + k * kstep, idesc, 1);
           }
           umma2_commit_both(&empty[stage]);                      // both CTAs may refill this stage
           if (kb == nkb - 1) umma2_commit_both(&acc_full[acc]);  // both epilogues may drain
@@ -238,6 +274,21 @@ tc2_gemm_nt_kernel(const __grid_constant__ Maps maps, const Params P) {
             l.w = __uint_as_float(to_tf32(v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u)));
             lo[c] = l;
           }
+          if (P.tn) {                   // the X half is raw too: its remainder goes beside it
+            const float4* bh = reinterpret_cast<const float4*>(st + 2 * A_BYTES);
+            float4* bl = reinterpret_cast<float4*>(st + 2 * A_BYTES + BH_BYTES);
+#pragma unroll
+            for (int i = 0; i < BH_BYTES / 16 / 128; ++i) {
+              const int c = t + i * 128;
+              const float4 v = bh[c];
+              float4 l;
+              l.x = __uint_as_float(to_tf32(v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u)));
+              l.y = __uint_as_float(to_tf32(v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u)));
+              l.z = __uint_as_float(to_tf32(v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u)));
+              l.w = __uint_as_float(to_tf32(v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u)));
+              bl[c] = l;
+            }
+          }
         }
         fence_proxy_async();            // this thread's generic-proxy writes -> visible to the tensor-core proxy
         __syncwarp();
@@ -257,6 +308,7 @@ tc2_gemm_nt_kernel(const __grid_constant__ Maps maps, const Params P) {
       const GemmNT& g = P.g[w.p];
       const bool vec_c = (g.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
       const bool vec_x = g.aux && (g.ldaux & 3) == 0 && ((reinterpret_cast<uintptr_t>(g.aux) & 15) == 0);
+      float* const Cbase = g.C + (P.tn ? (size_t)w.z * P.tn_nn * P.tn_kk : (size_t)0);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int m0 = w.m0 + (int)rank * BM, n0 = w.n0;
@@ -312,7 +364,7 @@ tc2_gemm_nt_kernel(const __grid_constant__ Maps maps, const Params P) {
               else v[j] = v[j] + x[j];
               if (n + j >= g.n_valid) v[j] = 0.f;
             }
-            float* dst = g.C + (size_t)m * g.ldc + n;
+            float* dst = Cbase + (size_t)m * g.ldc + n;
             if (vec_c && n + 3 < g.n_store) {
               *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
             } else {
@@ -347,10 +399,10 @@ bool tc2_eligible(const GemmNT& p) {
          (reinterpret_cast<uintptr_t>(p.B_lo) & 15) == 0;
 }
 
-// up to MAXP independent NT problems (pre-split weights) in one persistent launch of CTA pairs
-int gemm_nt_tc2_group(const GemmNT* ps, int n, cudaStream_t st) {
+// cluster launch of CTA pairs; the number of co-resident pairs is queried once (pairs must sit on one TPC, so it can
+// be below SMs / 2)
+static int pair_launch(const tc2::Maps& maps, const tc2::Params& P, int items, cudaStream_t st) {
   using namespace tc2;
-  if (n < 1 || n > MAXP) { set_error("gemm_nt_tc2_group: %d problems (max %d)", n, MAXP); return -2; }
   static int max_clusters = 0;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -371,11 +423,22 @@ int gemm_nt_tc2_group(const GemmNT* ps, int n, cudaStream_t st) {
     GIB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     cfg.gridDim = dim3(sms & ~1, 1, 1);
     int nc = 0;
-    // CTA pairs must sit on one TPC: the number of co-resident pairs can be below SMs / 2
     GIB_CUDA_TRY(cudaOccupancyMaxActiveClusters(&nc, tc2_gemm_nt_kernel, &cfg));
-    if (nc < 1) { set_error("gemm_nt_tc2: no CTA pair fits on this device"); return -4; }
+    if (nc < 1) { set_error("gemm_tc2: no CTA pair fits on this device"); return -4; }
     max_clusters = nc < sms / 2 ? nc : sms / 2;
   }
+  const int clusters = items < max_clusters ? items : max_clusters;
+  cfg.gridDim = dim3(2 * clusters, 1, 1);
+  GIB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc2_gemm_nt_kernel, maps, P));
+  ++g_launch_count;
+  return 0;
+}
+static int pair_capacity() { return 74; }   // planning figure for split counts (148 SMs); the launch clamps to the real one
+
+// up to MAXP independent NT problems (pre-split weights) in one persistent launch of CTA pairs
+int gemm_nt_tc2_group(const GemmNT* ps, int n, cudaStream_t st) {
+  using namespace tc2;
+  if (n < 1 || n > MAXP) { set_error("gemm_nt_tc2_group: %d problems (max %d)", n, MAXP); return -2; }
   Maps maps;
   Params P;
   memset(&P, 0, sizeof(P));
@@ -385,9 +448,9 @@ int gemm_nt_tc2_group(const GemmNT* ps, int n, cudaStream_t st) {
     const GemmNT& p = ps[i];
     if (p.M <= 0 || p.N <= 0) continue;
     if (!tc2_eligible(p)) { set_error("gemm_nt_tc2: needs TMA-aligned operands and pre-split weight planes"); return -2; }
-    GIB_TRY(tc_make_map(&maps.a[np], p.A, p.M, p.K, p.lda, BM));
-    GIB_TRY(tc_make_map(&maps.b_hi[np], p.B_hi, p.N, p.K, p.ldb, BNH));
-    GIB_TRY(tc_make_map(&maps.b_lo[np], p.B_lo, p.N, p.K, p.ldb, BNH));
+    GIB_TRY(tc_make_map(&maps.a[np], p.A, p.M, p.K, p.lda, BM, 0));
+    GIB_TRY(tc_make_map(&maps.b_hi[np], p.B_hi, p.N, p.K, p.ldb, BNH, 0));
+    GIB_TRY(tc_make_map(&maps.b_lo[np], p.B_lo, p.N, p.K, p.ldb, BNH, 0));
     P.g[np] = p;
     P.m_pairs[np] = ceil_div(p.M, 2 * BM);
     P.n_tiles[np] = ceil_div(p.N, BN);
@@ -401,11 +464,40 @@ int gemm_nt_tc2_group(const GemmNT* ps, int n, cudaStream_t st) {
   for (int i = np; i <= MAXP; ++i) P.item_begin[i] = items;
   P.nprob = np;
   P.debug = g_tc_debug;
-  const int clusters = items < max_clusters ? items : max_clusters;
-  cfg.gridDim = dim3(2 * clusters, 1, 1);
   ProfScope prof(PROF_GEMM_NT, work, st);
-  GIB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc2_gemm_nt_kernel, maps, P));
-  ++g_launch_count;
+  return pair_launch(maps, P, items, st);
+}
+
+// weight-gradient partial products into q.scratch ([splits][Nn][Kk]); the caller reduces them (reduce_grads_kernel).
+// Never more splits than tc_dw_plan() chose: the scratch halves are sized for that plan.
+int gemm_dw_tc2_partials(const GemmDW& q, int* splits_out, cudaStream_t st) {
+  using namespace tc2;
+  int plan_splits, plan_chunk;
+  tc_dw_plan(q.M, q.Nn, q.Kk, &plan_splits, &plan_chunk);
+  const int tiles = ceil_div(q.Nn, 2 * BM) * ceil_div(q.Kk, BN);
+  int s = ceil_div(pair_capacity(), tiles);
+  if (s > plan_splits) s = plan_splits;
+  if (s < 1) s = 1;
+  int chunk = ceil_div(ceil_div(q.M, s), BKF) * BKF;
+  if (chunk < 8 * BKF) chunk = 8 * BKF;
+  if (chunk < plan_chunk) chunk = plan_chunk;
+  const int splits = ceil_div(q.M, chunk);
+  Maps maps;
+  GIB_TRY(tc_make_map(&maps.a[0], q.G, q.M, q.Nn, q.ldg, BKF, 1));     // 32 reduction rows x 32 floats
+  GIB_TRY(tc_make_map(&maps.b_hi[0], q.X, q.M, q.Kk, q.ldx, BKF, 1));
+  Params P;
+  memset(&P, 0, sizeof(P));
+  GemmNT& g = P.g[0];
+  g = GemmNT();
+  g.C = q.scratch; g.ldc = q.Kk; g.M = q.Nn; g.N = q.Kk; g.n_store = q.Kk; g.n_valid = q.Kk;
+  g.mode = EPI_ACT; g.act = ACT_NONE; g.bias = nullptr;
+  P.m_pairs[0] = ceil_div(q.Nn, 2 * BM);
+  P.n_tiles[0] = ceil_div(q.Kk, BN);
+  P.nprob = 1;
+  P.tn = 1; P.splits = splits; P.chunk_rows = chunk; P.tn_rows = q.M; P.tn_nn = q.Nn; P.tn_kk = q.Kk;
+  P.debug = g_tc_debug;
+  GIB_TRY(pair_launch(maps, P, P.m_pairs[0] * P.n_tiles[0] * splits, st));
+  *splits_out = splits;
   return 0;
 }
 
