@@ -90,6 +90,10 @@ def _load():
 
 lib = _load()
 LIB_PATH = _build.LIB
+# diagnosis only: GIB_TC_DEBUG=<mask> selects a tcgen05 GEMM variant for the whole process (include/gib200.h,
+# gib_tc_debug) so that any test or tool can be re-run against it; unset = the product kernels
+if os.environ.get("GIB_TC_DEBUG"):
+    lib.gib_tc_debug(int(os.environ["GIB_TC_DEBUG"], 0))
 
 
 def check(rc, what=""):
