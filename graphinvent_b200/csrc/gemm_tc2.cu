@@ -7,10 +7,10 @@
 // A 128x128x32 k-block moves 192 KB through one SM's shared memory (TMA fill 48 KB, splitter 16 + 32 KB, three
 // MMAs x (A 16 KB + B 16 KB)) = 1536 cycles at 128 B/clk against 768 MMA cycles.  With a CTA pair on one TPC the
 // MMA is 256 x 128: each CTA keeps its own 128 rows of A and only HALF of the B tile (64 weight rows); the tensor
-// cores of both SMs read each half once.  Per SM and k-block: TMA fill 32 KB, splitter 16 + 16 KB (the raw tile is
-// the hi operand -- the MMA reads its top 19 bits -- so only the rounded remainder is written), MMA reads
-// 3 x (16 + 8) KB = 136 KB = 1088 cycles, and the weight traffic L2 -> SM halves.  The freed 16 KB per stage buy a
-// 4th pipeline stage.
+// cores of both SMs read each half once.  Per SM and k-block: TMA fill 32 KB, splitter 16 + 16 KB (with
+// gib_tc_debug bit 6 the raw tile is the hi operand -- the MMA reads its top 19 bits -- and only the rounded
+// remainder is written; otherwise hi is rounded in place, + 16 KB), MMA reads 3 x (16 + 8) KB: 136 KB = 1088 cycles,
+// and the weight traffic L2 -> SM halves.  The freed 16 KB per stage buy a 4th pipeline stage.
 //
 // Roles per CTA (same thread layout as gemm_tc.cu): warp 0 TMA producer (own A rows + own half of B_hi / B_lo),
 // warps 2-5 splitters (A only; weights arrive pre-split from the packed arena), warp 1 MMA issuer (leader CTA only;
@@ -134,6 +134,32 @@ __device__ __forceinline__ Item decode_item(const Params& P, int item) {
   return it;
 }
 
+// raw fp32 tile -> TF32 (hi, lo) pair, 128 threads.  SPLIT 1: hi = rna(x) written in place, lo = rna(x - hi);
+// SPLIT 2: the raw tile stays (the MMA reads its top 19 bits = truncation), lo = rna(x - trunc(x)).
+template <int SPLIT, int BYTES>
+__device__ __forceinline__ void split_tile(uint8_t* hi_raw, uint8_t* lo_out, int t) {
+  float4* hi = reinterpret_cast<float4*>(hi_raw);
+  float4* lo = reinterpret_cast<float4*>(lo_out);
+#pragma unroll
+  for (int i = 0; i < BYTES / 16 / 128; ++i) {
+    const int c = t + i * 128;
+    const float4 v = hi[c];
+    float4 h, l;
+    if (SPLIT == 2) {
+      h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+      h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+    } else {
+      h.x = __uint_as_float(to_tf32(v.x)); h.y = __uint_as_float(to_tf32(v.y));
+      h.z = __uint_as_float(to_tf32(v.z)); h.w = __uint_as_float(to_tf32(v.w));
+      hi[c] = h;
+    }
+    l.x = __uint_as_float(to_tf32(v.x - h.x)); l.y = __uint_as_float(to_tf32(v.y - h.y));
+    l.z = __uint_as_float(to_tf32(v.z - h.z)); l.w = __uint_as_float(to_tf32(v.w - h.w));
+    lo[c] = l;
+  }
+}
+
+template <int SPLIT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc2_gemm_nt_kernel(const __grid_constant__ Maps maps, const Params P) {
   extern __shared__ uint8_t smem_raw[];
@@ -251,7 +277,7 @@ tc2_gemm_nt_kernel(const __grid_constant__ Maps maps, const Params P) {
       }
     }
   } else if (warp < 6) {
-    // ================= splitters (both CTAs): lo = rna(x - trunc(x)) beside the raw tile =================
+    // ================= splitters (both CTAs) =================
     const int t = threadIdx.x - 64;   // 0..127
     int stage = 0;
     uint32_t phase = 0;
@@ -261,34 +287,8 @@ tc2_gemm_nt_kernel(const __grid_constant__ Maps maps, const Params P) {
         mbar_wait(&full_raw[stage], phase);
         uint8_t* st = smem + stage * STAGE_BYTES;
         if (!(P.debug & 1)) {
-          const float4* hi = reinterpret_cast<const float4*>(st);
-          float4* lo = reinterpret_cast<float4*>(st + A_BYTES);
-#pragma unroll
-          for (int i = 0; i < A_BYTES / 16 / 128; ++i) {
-            const int c = t + i * 128;
-            const float4 v = hi[c];
-            float4 l;
-            l.x = __uint_as_float(to_tf32(v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u)));
-            l.y = __uint_as_float(to_tf32(v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u)));
-            l.z = __uint_as_float(to_tf32(v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u)));
-            l.w = __uint_as_float(to_tf32(v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u)));
-            lo[c] = l;
-          }
-          if (P.tn) {                   // the X half is raw too: its remainder goes beside it
-            const float4* bh = reinterpret_cast<const float4*>(st + 2 * A_BYTES);
-            float4* bl = reinterpret_cast<float4*>(st + 2 * A_BYTES + BH_BYTES);
-#pragma unroll
-            for (int i = 0; i < BH_BYTES / 16 / 128; ++i) {
-              const int c = t + i * 128;
-              const float4 v = bh[c];
-              float4 l;
-              l.x = __uint_as_float(to_tf32(v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u)));
-              l.y = __uint_as_float(to_tf32(v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u)));
-              l.z = __uint_as_float(to_tf32(v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u)));
-              l.w = __uint_as_float(to_tf32(v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u)));
-              bl[c] = l;
-            }
-          }
+          split_tile<SPLIT, A_BYTES>(st, st + A_BYTES, t);
+          if (P.tn) split_tile<SPLIT, BH_BYTES>(st + 2 * A_BYTES, st + 2 * A_BYTES + BH_BYTES, t);   // X half is raw too
         }
         fence_proxy_async();            // this thread's generic-proxy writes -> visible to the tensor-core proxy
         __syncwarp();
@@ -417,19 +417,21 @@ static int pair_launch(const tc2::Maps& maps, const tc2::Params& P, int items, c
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   if (max_clusters == 0) {
-    GIB_CUDA_TRY(cudaFuncSetAttribute(tc2_gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    GIB_CUDA_TRY(cudaFuncSetAttribute(tc2_gemm_nt_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    GIB_CUDA_TRY(cudaFuncSetAttribute(tc2_gemm_nt_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     int dev = 0, sms = 0;
     GIB_CUDA_TRY(cudaGetDevice(&dev));
     GIB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     cfg.gridDim = dim3(sms & ~1, 1, 1);
     int nc = 0;
-    GIB_CUDA_TRY(cudaOccupancyMaxActiveClusters(&nc, tc2_gemm_nt_kernel, &cfg));
+    GIB_CUDA_TRY(cudaOccupancyMaxActiveClusters(&nc, tc2_gemm_nt_kernel<1>, &cfg));
     if (nc < 1) { set_error("gemm_tc2: no CTA pair fits on this device"); return -4; }
     max_clusters = nc < sms / 2 ? nc : sms / 2;
   }
   const int clusters = items < max_clusters ? items : max_clusters;
   cfg.gridDim = dim3(2 * clusters, 1, 1);
-  GIB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc2_gemm_nt_kernel, maps, P));
+  if (g_tc_debug & 64) GIB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc2_gemm_nt_kernel<2>, maps, P));   // raw hi operand
+  else GIB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc2_gemm_nt_kernel<1>, maps, P));
   ++g_launch_count;
   return 0;
 }
