@@ -135,7 +135,8 @@ class GraphGeneratorRL(GraphGenerator):
             raise ValueError("batch_size must stay below 2**24 (slot ids travel as fp32)")
         self._allocate()                                    # a fresh rollout (the reference builds a new generator)
         tags = torch.arange(1, B + 1, dtype=torch.float32, device=self.device)
-        share = type(agent) is type(prior) and Fn.dims_key(agent, B) == Fn.dims_key(prior, B)
+        fused = [hasattr(m, "dims") for m in (agent, prior)]      # this package's modules take a shared K0
+        share = all(fused) and type(agent) is type(prior) and Fn.dims_key(agent, B) == Fn.dims_key(prior, B)
         lik_a, lik_p = [], []
         n_generated, rnd = 0, 0
         replay = iter(replay) if replay is not None else None
@@ -146,9 +147,9 @@ class GraphGeneratorRL(GraphGenerator):
                                    "(GraphGeneratorRL.py:175, 'the 2 is arbitrary') would overflow, as in the reference")
             # the round kernel edits the batch in place while autograd keeps the inputs of every round: snapshot them
             nodes_in, edges_in = self.nodes.clone(), self.edges.clone()
-            graph = Fn.build_graph(agent, edges_in)
-            out_a = agent(nodes_in, edges_in, graph=graph)                             # GraphGeneratorRL.py:131-132
-            out_p = prior(nodes_in, edges_in, graph=graph if share else None)
+            graph = Fn.build_graph(agent, edges_in) if share else None
+            out_a = agent(nodes_in, edges_in, graph=graph) if share else agent(nodes_in, edges_in)   # GraphGeneratorRL.py:131-132
+            out_p = prior(nodes_in, edges_in, graph=graph) if share else prior(nodes_in, edges_in)
             if replay is not None:
                 try:
                     action = next(replay)
