@@ -60,6 +60,31 @@ __global__ void __launch_bounds__(256) kl_loss_kernel(const float* __restrict__ 
   if (threadIdx.x == 0 && loss_rows) loss_rows[b] = acc;
 }
 
+// ---- validation NLL per sub-graph (Analyzer.get_validation_likelihood, Analyzer.py:744-758):
+//      nll[b] = -log( sum_k softmax(out[b])_k * target[b,k] / sum(target[b]) );  an all-zero target row gives NaN,
+//      which the reference filters out afterwards (Analyzer.py:756) -----------------------------------------------
+__global__ void __launch_bounds__(256) validation_nll_kernel(const float* __restrict__ out,
+                                                             const float* __restrict__ target, int apd,
+                                                             float* __restrict__ nll) {
+  __shared__ float sm[8];
+  const int b = blockIdx.x;
+  const float* o = out + (size_t)b * apd;
+  const float* t = target + (size_t)b * apd;
+  float mx = -INFINITY, ts = 0.f;
+  for (int k = threadIdx.x; k < apd; k += 256) { mx = fmaxf(mx, o[k]); ts += t[k]; }
+  mx = block_reduce<256>(mx, sm, true);
+  ts = block_reduce<256>(ts, sm, false);
+  float se = 0.f, dot = 0.f;
+  for (int k = threadIdx.x; k < apd; k += 256) {
+    const float e = expf(o[k] - mx);
+    se += e;
+    dot += e * t[k];
+  }
+  se = block_reduce<256>(se, sm, false);
+  dot = block_reduce<256>(dot, sm, false);
+  if (threadIdx.x == 0) nll[b] = -logf((dot / se) / ts);     // ts == 0 -> 0/0 = NaN like target/sum(target)
+}
+
 // ---- categorical sampling of one action per molecule (GraphGenerator.py:121, 535-542) ----
 __global__ void __launch_bounds__(256) sample_actions_kernel(const float* __restrict__ out, int apd,
                                                              const float* __restrict__ uniforms,
@@ -212,6 +237,13 @@ int gib_kl_loss_fwd_bwd(const float* out, const float* target, int B, int apd, f
                         float* dout, gib_stream stream) {
   if (B <= 0) return 0;
   kl_loss_kernel<<<B, 256, 0, ST(stream)>>>(out, target, apd, grad_scale, loss_rows, dout);
+  GIB_LAUNCH_CHECK();
+  return 0;
+}
+
+int gib_validation_nll(const float* out, const float* target, int B, int apd, float* nll, gib_stream stream) {
+  if (B <= 0) return 0;
+  validation_nll_kernel<<<B, 256, 0, ST(stream)>>>(out, target, apd, nll);
   GIB_LAUNCH_CHECK();
   return 0;
 }

@@ -228,6 +228,19 @@ def kl_loss(output, target):
     return _KLLoss.apply(output.contiguous().float(), target.contiguous().float())
 
 
+def validation_nll(output, target):
+    """per-row NLL of the "correct" actions, the inner loop body of `Analyzer.get_validation_likelihood`
+    (Analyzer.py:744-758): -log(sum(softmax(output) * target / sum(target))) in one kernel; NaN for all-zero target
+    rows (filter with `nll[~torch.isnan(nll)]` as the reference does at :756).  No gradient (evaluation only)."""
+    _require_cuda(output, target)
+    B, apd = output.shape
+    out = output.detach().contiguous().float()
+    tgt = target.contiguous().float()
+    nll = torch.empty(B, dtype=torch.float32, device=out.device)
+    check(lib.gib_validation_nll(_ptr(out), _ptr(tgt), B, apd, _ptr(nll), _stream(out.device)), "gib_validation_nll")
+    return nll
+
+
 def sample_actions(output, uniforms=None, generator=None):
     """softmax + one categorical draw per molecule from APD logits (GraphGenerator.py:121,535-542),
     inverse-CDF on uniforms in [0,1).  Returns (flat action index int32 [B], likelihood [B])."""

@@ -124,6 +124,11 @@ int gib_model_backward(const gib_dims* d, const int* hdr_host, const float* node
 int gib_kl_loss_fwd_bwd(const float* out, const float* target, int B, int apd, float grad_scale,
                         float* loss_rows, float* dout, gib_stream stream);
 
+/* ---- validation NLL of the "correct" actions (Analyzer.get_validation_likelihood, Analyzer.py:744-758), one kernel:
+ *      nll[b] = -log( sum_k softmax(out[b])_k * target[b,k] / sum_k target[b,k] ).  Rows with an all-zero target
+ *      give NaN (the reference drops them afterwards, Analyzer.py:756). -------------------------------------- */
+int gib_validation_nll(const float* out, const float* target, int B, int apd, float* nll, gib_stream stream);
+
 /* ---- flat-bucket Adam step: replaces torch.optim.Adam.step() on the model parameters (constructed at
  *      Workflow.py:191,221,245, stepped at Workflow.py:795-796; same update rule, L2 weight decay, no amsgrad)
  *      with ONE launch over contiguous params / grads / exp_avg / exp_avg_sq of n floats.  `step` is the

@@ -86,3 +86,22 @@ def test_rl_rollout_replay_matches_the_reference_trace():
                 ref = torch.from_numpy(z[key])
                 assert (p.grad.cpu() - ref).norm().item() <= 5e-2 * ref.norm().item() + 1e-3 * total, (tag, k)
         assert abs(got_sq ** 0.5 - total) <= 2e-2 * total
+
+
+@pytest.mark.gpu
+def test_validation_nll_matches_the_reference_expression():
+    """Analyzer.get_validation_likelihood's per-row NLL (Analyzer.py:744-758) in one kernel, incl. the NaN rows the
+    reference filters out"""
+    from graphinvent_b200 import functional as Fn
+    g = torch.Generator().manual_seed(4)
+    out = 3.0 * torch.randn(300, 625, generator=g)
+    target = (torch.rand(300, 625, generator=g) < 0.01).float()
+    target[7] = 0.0                                            # all-zero target row -> NaN, dropped by the caller
+    target[8] = 0.0
+    target[8, -1] = 1.0                                        # a "terminate" sub-graph
+    renorm = target / target.sum(1, keepdim=True)
+    ref = -torch.log((renorm * torch.softmax(out.double(), 1)).sum(1))
+    got = Fn.validation_nll(out.cuda(), target.cuda()).cpu()
+    assert torch.isnan(got[7]) and torch.isnan(ref[7])
+    keep = ~torch.isnan(ref)
+    assert (got[keep].double() - ref[keep]).abs().max().item() <= 1e-5 * max(1.0, ref[keep].abs().max().item())
