@@ -6,13 +6,13 @@ import pytest
 import torch
 
 from tests import hostshim
-from tests.conftest import load_small
+from tests.conftest import MODELS, load_small
 
 
-@pytest.fixture
-def net_and_lib(monkeypatch):
+@pytest.fixture(params=MODELS)
+def net_and_lib(request, monkeypatch):
     from graphinvent_b200.gnn import mpnn
-    fx = load_small("GGNN")
+    fx = load_small(request.param)
     net = mpnn.create(fx["C"])
     net.load_state_dict(fx["sd"])
     return net, hostshim.install_model_shims(monkeypatch, net), fx
