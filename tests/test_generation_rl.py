@@ -143,3 +143,64 @@ def test_rl_generator_host_logic_on_cpu_shims(monkeypatch, seed):
     with torch.no_grad():
         out = gen.sample(agent, prior, generator=torch.Generator().manual_seed(3))
     assert not out[1].requires_grad and torch.isfinite(out[1]).all() and int(gen._counters[0]) >= B
+
+
+class _OracleModel(torch.nn.Module):
+    """the CPU oracle's functional forward behind the module call protocol (parameters = the state_dict)"""
+
+    def __init__(self, C, sd):
+        super().__init__()
+        self.C = C
+        self.names = list(sd)
+        self.params = torch.nn.ParameterList([torch.nn.Parameter(v.clone()) for v in sd.values()])
+
+    def forward(self, nodes, edges, graph=None):
+        from oracle import mpnn_oracle as O
+        return O.forward(dict(zip(self.names, self.params)), self.C, nodes, edges)
+
+
+def test_rl_generator_with_oracle_models_reproduces_the_reference_trace(monkeypatch):
+    """end to end on CPU: this package's GraphGeneratorRL (round kernel played by the generation oracle, models
+    played by the MPNN oracle with the shipped checkpoint) replays the reference's draws and must land on the
+    reference's own numbers -- both likelihood streams, the log-likelihoods, the RL loss and the gradients that
+    flow back through all 16 rounds into both models"""
+    from tests.conftest import pretrained_path
+    path = pretrained_path()
+    if path is None:
+        pytest.skip("tests/golden/_local/pretrained_model.pth absent")
+    from oracle import mpnn_oracle as O
+    from tests import hostshim
+    from graphinvent_b200.config import make_constants
+    from graphinvent_b200.generation import GraphGeneratorRL
+    hostshim.install_generation_shims(monkeypatch)
+    z = _trace()
+    B, n_gen, R = int(z["batch"]), int(z["n_generated"]), int(z["rounds"])
+    sd = torch.load(path, map_location="cpu", weights_only=False)
+    g = torch.Generator().manual_seed(int(z["prior_seed"]))
+    sd_prior = {k: v + float(z["prior_noise"]) * torch.randn(v.shape, generator=g) for k, v in sd.items()}
+    C = O.make_constants("GGNN")
+    agent, prior = _OracleModel(C, sd), _OracleModel(C, sd_prior)
+    gen = GraphGeneratorRL(None, B, constants=make_constants("GGNN"), n_atom_types=A, n_formal_charge=CH, device="cpu")
+    _, agent_ll, prior_ll, proper = gen.sample(agent, prior, replay=[torch.from_numpy(a) for a in z["actions"]])
+    assert gen.rounds == R and int(gen._counters[0]) == n_gen
+    assert (gen.generated_nodes.numpy().astype(np.int8) == z["generated_nodes"]).all()
+    assert (gen.generated_edges.numpy().astype(np.int8) == z["generated_edges"]).all()
+    assert (gen.properly_terminated.numpy() == z["properly_terminated"]).all()
+    assert np.abs(gen.generated_agent_likelihoods.detach().numpy() - z["generated_agent_likelihoods"]).max() <= 5e-6
+    assert np.abs(gen.generated_prior_likelihoods.detach().numpy() - z["generated_prior_likelihoods"]).max() <= 5e-6
+    assert np.abs(agent_ll.detach().numpy() - z["agent_loglikelihoods"]).max() <= 1e-5
+    assert np.abs(prior_ll.detach().numpy() - z["prior_loglikelihoods"]).max() <= 1e-5
+    scores = torch.tensor([((i * 37) % 10) / 10.0 for i in range(B)])
+    diff = agent_ll - (prior_ll + float(z["sigma"]) * scores)
+    loss = torch.mean(diff * diff)
+    assert abs(loss.item() - float(z["loss"])) <= 1e-4 * float(z["loss"])
+    loss.backward()
+    for tag, net in (("agent", agent), ("prior", prior)):
+        ref = dict(zip([str(s) for s in z[f"grad_names_{tag}"]], z[f"grad_norm_{tag}"]))
+        total = float(np.linalg.norm(z[f"grad_norm_{tag}"]))
+        for k, p in zip(net.names, net.params):
+            assert abs(p.grad.norm().item() - ref[k]) <= 1e-3 * ref[k] + 1e-5 * total, (tag, k)
+            key = f"grad_{tag}/{k}"
+            if key in z.files:
+                want = torch.from_numpy(z[key])
+                assert (p.grad - want).norm().item() <= 1e-3 * want.norm().item() + 1e-5 * total, (tag, k)
