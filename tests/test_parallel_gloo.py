@@ -49,7 +49,8 @@ def _worker(rank, world, port, q):
         hook.set_shard(hi2 - lo2, 10)
         flat2 = data[lo2:hi2].mean(0).clone()
         model._grad_hook(flat2)
-        q.put((rank, model.w.detach().clone(), flat, want_equal, flat2, hook.calls, hook.bytes))
+        # plain lists, not tensors: a tensor travels as a shared-memory handle that dies with this process
+        q.put((rank, model.w.detach().tolist(), flat.tolist(), want_equal.tolist(), flat2.tolist(), hook.calls, hook.bytes))
     finally:
         dist.destroy_process_group()
 
@@ -80,6 +81,7 @@ def test_flat_bucket_allreduce_world2_gloo():
         res = _run_world2()
     except Exception:             # the probed rendezvous port can be taken in between: one retry on a fresh port
         res = _run_world2()
+    res = [(r, torch.tensor(w), torch.tensor(f), torch.tensor(wa), torch.tensor(f2), c, nb) for r, w, f, wa, f2, c, nb in res]
     for rank, w, flat, want, flat2, calls, nbytes in res:
         assert torch.equal(w, torch.ones(5))                      # broadcast from rank 0
         assert torch.allclose(flat, want, atol=1e-6)              # mean of equal shards == global mean
