@@ -7,7 +7,6 @@ No computation of the hot path happens in ATen, and there is no CPU path: CPU te
 """
 import ctypes
 
-import numpy as np
 import torch
 
 from ._lib import Dims, HDR_E, HDR_FLAGS, HDR_INTS, HDR_P, MODEL_ID, check, lib

@@ -5,7 +5,6 @@ contiguously across ranks, parameters are replicated, and the only exchange is O
 of the flat gradient bucket per step (NCCL over NVLink on the GPU box; gloo in the CPU tests).
 The reference has no multi-GPU path; generation needs no communication at all.
 """
-import torch
 import torch.distributed as dist
 
 

@@ -1,7 +1,6 @@
 """GPU: every kernel family through the C-ABI against the ATen expression it replaces."""
 import ctypes
 
-import numpy as np
 import pytest
 import torch
 

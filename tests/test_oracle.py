@@ -1,6 +1,5 @@
 """CPU: the oracle (oracle/mpnn_oracle.py) against the golden fixtures produced by the
 unmodified reference, and against the live reference when /root/reference is mounted."""
-import numpy as np
 import pytest
 import torch
 

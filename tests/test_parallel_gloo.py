@@ -3,7 +3,6 @@ sharding + the single flat-bucket gradient all-reduce).  On the GPU box the same
 import os
 import socket
 
-import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
