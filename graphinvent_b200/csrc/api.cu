@@ -270,6 +270,13 @@ int gib_linear_fwd_tc(const float* X, int ldx, const float* W, int ldw, const fl
   p.act = act; p.mode = EPI_ACT; p.n_store = N; p.n_valid = N;
   return gemm_nt_tc(p, ST(stream));
 }
+int gib_linear_fwd_tc_planes(const float* X, int ldx, const float* W_hi, const float* W_lo, int ldw, const float* bias,
+                             float* Y, int ldy, int M, int N, int K, int act, gib_stream stream) {
+  GemmNT p;
+  p.A = X; p.lda = ldx; p.B = W_hi; p.B_hi = W_hi; p.B_lo = W_lo; p.ldb = ldw; p.C = Y; p.ldc = ldy;
+  p.M = M; p.N = N; p.K = K; p.bias = bias; p.act = act; p.mode = EPI_ACT; p.n_store = N; p.n_valid = N;
+  return gemm_nt_tc(p, ST(stream));
+}
 size_t gib_dw_scratch_bytes(int M, int Nn, int Kk) { return gemm_dw_scratch_floats(M, Nn, Kk) * sizeof(float); }
 int gib_linear_bwd_dw(const float* G, int ldg, int Nn, const float* X, int ldx, int Kk, int M, float* dW, float* dbias,
                       int R, int C, void* scratch, gib_stream stream) {

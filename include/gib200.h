@@ -146,6 +146,12 @@ int gib_linear_fwd(const float* X, int ldx, const float* W, int ldw, const float
 /* same contract, forced onto the tcgen05 3xTF32 kernel regardless of the size heuristics */
 int gib_linear_fwd_tc(const float* X, int ldx, const float* W, int ldw, const float* bias, float* Y, int ldy,
                       int M, int N, int K, int act, gib_stream stream);
+/* the model's own call pattern: W arrives as its TF32 hi / lo planes (hi = rna(W), lo = rna(W - hi), as
+ * gib_model_pack lays them out), only X is split in the kernel.  With gib_tc_debug bit 7 this is the entry that
+ * reaches the CTA-pair kernel for a single GEMM. */
+int gib_linear_fwd_tc_planes(const float* X, int ldx, const float* W_hi, const float* W_lo, int ldw,
+                             const float* bias, float* Y, int ldy, int M, int N, int K, int act,
+                             gib_stream stream);
 /* dW[R,C] += G^T X, dbias[R] += colsum(G); G [M, ldg], X [M, ldx]; scratch from gib_dw_scratch_bytes */
 size_t gib_dw_scratch_bytes(int M, int Nn, int Kk);
 int gib_linear_bwd_dw(const float* G, int ldg, int Nn, const float* X, int ldx, int Kk, int M, float* dW,
