@@ -72,3 +72,29 @@ def test_oracle_matches_live_reference(model):
         ref = net(nodes, edges)
         out = O.forward(sd, C, nodes, edges)
     assert (out - ref).abs().max().item() <= LOGIT_TOL
+
+
+@pytest.mark.parametrize("model", MODELS)
+def test_oracle_training_curve_follows_the_reference(model):
+    """50 steps of Workflow.train_epoch (Adam + OneCycleLR) with the oracle's functional forward against the curve
+    of the unmodified reference (tests/golden/make_loss_curves.py); SURVEY.md 8c tolerance 1e-4"""
+    import os
+
+    import numpy as np
+    from tests.conftest import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "loss_curves.npz"))
+    fx = load_small(model)
+    sd = {k: torch.nn.Parameter(v.clone()) for k, v in fx["sd"].items()}
+    steps = int(z["steps"])
+    opt = torch.optim.Adam(list(sd.values()), lr=float(z["lr"]))
+    sch = torch.optim.lr_scheduler.OneCycleLR(opt, max_lr=float(z["max_lr"]), total_steps=steps)
+    losses = []
+    for _ in range(steps):
+        opt.zero_grad()
+        loss = O.kl_loss(O.forward(sd, fx["C"], fx["nodes"], fx["edges"]), fx["target"])
+        loss.backward()
+        opt.step()
+        sch.step()
+        losses.append(loss.item())
+    dev = np.abs(np.array(losses) - z[f"loss/{model}"])
+    assert dev[0] <= 1e-6 and dev.max() <= 1e-4, (model, float(dev.max()))
