@@ -138,12 +138,11 @@ __device__ __forceinline__ Item decode_item(const Params& P, int item) {
 // SPLIT 2: the raw tile stays (the MMA reads its top 19 bits = truncation), lo = rna(x - trunc(x)).
 template <int SPLIT, int BYTES>
 __device__ __forceinline__ void split_tile(uint8_t* hi_raw, uint8_t* lo_out, int t) {
-  float4* hi = reinterpret_cast<float4*>(hi_raw);
-  float4* lo = reinterpret_cast<float4*>(lo_out);
+  const uint32_t hi = smem_u32(hi_raw), lo = smem_u32(lo_out);
 #pragma unroll
   for (int i = 0; i < BYTES / 16 / 128; ++i) {
-    const int c = t + i * 128;
-    const float4 v = hi[c];
+    const uint32_t c = (uint32_t)(t + i * 128) * 16;
+    const float4 v = lds128(hi + c);
     float4 h, l;
     if (SPLIT == 2) {
       h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
@@ -151,11 +150,11 @@ __device__ __forceinline__ void split_tile(uint8_t* hi_raw, uint8_t* lo_out, int
     } else {
       h.x = __uint_as_float(to_tf32(v.x)); h.y = __uint_as_float(to_tf32(v.y));
       h.z = __uint_as_float(to_tf32(v.z)); h.w = __uint_as_float(to_tf32(v.w));
-      hi[c] = h;
+      sts128(hi + c, h);
     }
     l.x = __uint_as_float(to_tf32(v.x - h.x)); l.y = __uint_as_float(to_tf32(v.y - h.y));
     l.z = __uint_as_float(to_tf32(v.z - h.z)); l.w = __uint_as_float(to_tf32(v.w - h.w));
-    lo[c] = l;
+    sts128(lo + c, l);
   }
 }
 
@@ -300,7 +299,7 @@ tc2_gemm_nt_kernel(const __grid_constant__ Maps maps, const Params P) {
     // ================= epilogue (both CTAs; same data path as gemm_tc.cu) =================
     const int q = warp & 3;
     const int half = (warp - 6) >> 2;
-    float* stg = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + BAR_BYTES) + (warp - 6) * (32 * EPI_LD);
+    const uint32_t stg_s = smem_u32(smem + STAGES * STAGE_BYTES + BAR_BYTES) + (uint32_t)(warp - 6) * (32 * EPI_LD * 4);
     const int rr = lane >> 2, cc = (lane & 3) * 4;
     int it = 0;
     for (int item = cluster_id; item < num_items; item += num_clusters, ++it) {
@@ -324,11 +323,11 @@ tc2_gemm_nt_kernel(const __grid_constant__ Maps maps, const Params P) {
         tmem_ld_wait();
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4)
-          *reinterpret_cast<float4*>(stg + lane * EPI_LD + j4 * 4) =
-              make_float4(__uint_as_float(r[j4 * 4 + 0]) + __uint_as_float(rx[j4 * 4 + 0]),
-                          __uint_as_float(r[j4 * 4 + 1]) + __uint_as_float(rx[j4 * 4 + 1]),
-                          __uint_as_float(r[j4 * 4 + 2]) + __uint_as_float(rx[j4 * 4 + 2]),
-                          __uint_as_float(r[j4 * 4 + 3]) + __uint_as_float(rx[j4 * 4 + 3]));
+          sts128(stg_s + (uint32_t)(lane * EPI_LD + j4 * 4) * 4,
+                 make_float4(__uint_as_float(r[j4 * 4 + 0]) + __uint_as_float(rx[j4 * 4 + 0]),
+                             __uint_as_float(r[j4 * 4 + 1]) + __uint_as_float(rx[j4 * 4 + 1]),
+                             __uint_as_float(r[j4 * 4 + 2]) + __uint_as_float(rx[j4 * 4 + 2]),
+                             __uint_as_float(r[j4 * 4 + 3]) + __uint_as_float(rx[j4 * 4 + 3])));
         __syncwarp();
         const int n = n0 + col0 + cc;
         if (n < g.n_store && !(P.debug & 2)) {
@@ -343,7 +342,7 @@ tc2_gemm_nt_kernel(const __grid_constant__ Maps maps, const Params P) {
             const int row = i * 8 + rr;
             const int m = m0 + q * 32 + row;
             if (m >= g.M) continue;
-            const float4 a4 = *reinterpret_cast<const float4*>(stg + row * EPI_LD + cc);
+            const float4 a4 = lds128(stg_s + (uint32_t)(row * EPI_LD + cc) * 4);
             float v[4] = {a4.x, a4.y, a4.z, a4.w};
             float x[4] = {0.f, 0.f, 0.f, 0.f};
             if (g.mode != EPI_ACT) {
