@@ -114,6 +114,7 @@ __device__ __forceinline__ Item decode_item(const Params& P, int item) {
 
 // SPLIT 0: hi = truncation, lo = exact remainder;  1: hi, lo both round-to-nearest (cvt.rna);
 //       2: hi = the raw value (the MMA reads its top 19 bits = truncation, nothing is written back), lo = rna(x - trunc(x))
+//       3: SPLIT 1 with explicit shared-window loads / stores in the splitters and the epilogue staging
 // TIMING: accumulate per-role wait / work cycles into P.timing (diagnosis builds; the product uses <1, false>)
 template <int SPLIT, bool TIMING = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -269,7 +270,25 @@ tc_gemm_nt_kernel(const __grid_constant__ Maps maps, const Params P) {
         long long t_w0 = 0;
         if constexpr (TIMING) t_w0 = clock64();
         uint8_t* st = smem + stage * STAGE_BYTES;
-        if (!(P.debug & 1)) {
+        if (SPLIT == 3) {
+          // same arithmetic as SPLIT 1 through explicit LDS.128 / STS.128 (the pointer form below compiles to
+          // generic LD.E / ST.E): isolates the cost of the generic address path
+          for (int op = 0; op < nops; ++op) {
+            const uint32_t hi_s = smem_u32(st + op * 2 * TILE_BYTES), lo_s = hi_s + TILE_BYTES;
+#pragma unroll
+            for (int i = 0; i < TILE_BYTES / 16 / 128; ++i) {
+              const uint32_t c = (uint32_t)(t + i * 128) * 16;
+              const float4 v = lds128(hi_s + c);
+              float4 h, l;
+              h.x = __uint_as_float(to_tf32(v.x)); l.x = __uint_as_float(to_tf32(v.x - h.x));
+              h.y = __uint_as_float(to_tf32(v.y)); l.y = __uint_as_float(to_tf32(v.y - h.y));
+              h.z = __uint_as_float(to_tf32(v.z)); l.z = __uint_as_float(to_tf32(v.z - h.z));
+              h.w = __uint_as_float(to_tf32(v.w)); l.w = __uint_as_float(to_tf32(v.w - h.w));
+              sts128(hi_s + c, h);
+              sts128(lo_s + c, l);
+            }
+          }
+        } else if (!(P.debug & 1)) {
           auto split_tile = [&](int op) {
             float4* hi = reinterpret_cast<float4*>(st + op * 2 * TILE_BYTES);
             float4* lo = reinterpret_cast<float4*>(st + op * 2 * TILE_BYTES + TILE_BYTES);
@@ -350,12 +369,14 @@ tc_gemm_nt_kernel(const __grid_constant__ Maps maps, const Params P) {
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + acc * 2 * BN + BN + col0, rx);
         tmem_ld_wait();
 #pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4)
-          *reinterpret_cast<float4*>(stg + lane * EPI_LD + j4 * 4) =
-              make_float4(__uint_as_float(r[j4 * 4 + 0]) + __uint_as_float(rx[j4 * 4 + 0]),
-                          __uint_as_float(r[j4 * 4 + 1]) + __uint_as_float(rx[j4 * 4 + 1]),
-                          __uint_as_float(r[j4 * 4 + 2]) + __uint_as_float(rx[j4 * 4 + 2]),
-                          __uint_as_float(r[j4 * 4 + 3]) + __uint_as_float(rx[j4 * 4 + 3]));
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 sum4 = make_float4(__uint_as_float(r[j4 * 4 + 0]) + __uint_as_float(rx[j4 * 4 + 0]),
+                                          __uint_as_float(r[j4 * 4 + 1]) + __uint_as_float(rx[j4 * 4 + 1]),
+                                          __uint_as_float(r[j4 * 4 + 2]) + __uint_as_float(rx[j4 * 4 + 2]),
+                                          __uint_as_float(r[j4 * 4 + 3]) + __uint_as_float(rx[j4 * 4 + 3]));
+          if constexpr (SPLIT == 3) sts128(smem_u32(stg + lane * EPI_LD + j4 * 4), sum4);
+          else *reinterpret_cast<float4*>(stg + lane * EPI_LD + j4 * 4) = sum4;
+        }
         __syncwarp();
         const int n = n0 + col0 + cc;
         if (n < g.n_store && !(P.debug & 2)) {
@@ -370,7 +391,9 @@ tc_gemm_nt_kernel(const __grid_constant__ Maps maps, const Params P) {
             const int row = i * 8 + rr;
             const int m = m0 + q * 32 + row;
             if (m >= g.M) continue;
-            const float4 a4 = *reinterpret_cast<const float4*>(stg + row * EPI_LD + cc);
+            float4 a4;
+            if constexpr (SPLIT == 3) a4 = lds128(smem_u32(stg + row * EPI_LD + cc));
+            else a4 = *reinterpret_cast<const float4*>(stg + row * EPI_LD + cc);
             float v[4] = {a4.x, a4.y, a4.z, a4.w};
             float x[4] = {0.f, 0.f, 0.f, 0.f};
             if (g.mode != EPI_ACT) {
@@ -473,7 +496,8 @@ int tc_make_map(void* map, const float* base, int rows, int cols, int ld, int bo
 
 bool g_use_tc = true;
 int g_tc_debug = 0;               // bit 2 (4): truncation split, bit 4 (16): ignore pre-split weights, bit 6 (64): SPLIT = 2,
-                                  // bit 7 (128): CTA-pair kernel (gemm_tc2.cu) for problems with pre-split weights
+                                  // bit 7 (128): CTA-pair kernel (gemm_tc2.cu) for problems with pre-split weights,
+                                  // bit 8 (256): SPLIT = 3 (explicit LDS / STS)
 long long* g_tc_timing = nullptr; // non-null: launch the TIMING instantiation, per-CTA role timings land here
 
 bool tc_eligible(const GemmNT& p) {
@@ -492,6 +516,7 @@ static int tc_prepare(int* num_sms_out) {
     GIB_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_nt_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     GIB_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_nt_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     GIB_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_nt_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    GIB_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_nt_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     GIB_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_nt_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     GIB_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_nt_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_done = true;
@@ -512,6 +537,8 @@ static void launch_tc(int grid, const tc::Maps& maps, tc::Params& P, cudaStream_
     tc_gemm_nt_kernel<0><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps, P);
   } else if (split2) {
     tc_gemm_nt_kernel<2><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps, P);
+  } else if (g_tc_debug & 256) {
+    tc_gemm_nt_kernel<3><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps, P);
   } else {
     tc_gemm_nt_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps, P);
   }

@@ -73,7 +73,8 @@ int gib_get_tensor_cores(void);
 /* diagnosis switches of the tcgen05 GEMM (process-wide, default 0).  Results stay correct with bit2 (truncation
  * split), bit4 (split the weights in the kernel instead of using the packed hi/lo planes) and bit6 (hi operand = raw
  * tile, only the rounded remainder is written); bit7 routes forward/dX GEMMs with packed weights to the CTA-pair
- * candidate kernel (cta_group::2); bit0 (skip the split) and bit1 (skip epilogue stores) are timing experiments
+ * candidate kernel (cta_group::2); bit8 = the product arithmetic with explicit shared-window loads / stores;
+ * bit0 (skip the split) and bit1 (skip epilogue stores) are timing experiments
  * whose results are wrong. */
 void gib_tc_debug(int mode);
 /* device_buf != NULL: every following tcgen05 GEMM launch runs its TIMING build and ADDS clock64 totals per role

@@ -4,7 +4,7 @@
     timeout 300 python tools/tc_variants.py 0 64       # a subset (gib_tc_debug masks)
 
 Variants (include/gib200.h): 0 product (round-to-nearest hi/lo split), 4 truncation split, 64 raw hi operand
-(SPLIT = 2), 128 CTA-pair kernel (gemm_tc2.cu, cta_group::2 -- first run: wrap in `timeout`, its waits trap after
+(SPLIT = 2), 256 product arithmetic with explicit LDS / STS (SPLIT = 3), 128 CTA-pair kernel (gemm_tc2.cu, cta_group::2 -- first run: wrap in `timeout`, its waits trap after
 ~10 s if a hand-off is wrong), 192 = 128 | 64 (pair kernel with the raw hi operand).
 For each: max |logit - reference| on the shipped checkpoint x 256 real gdb13 rows (bonded / bond-less, bar 1e-4),
 gradient norm-level deviation, and the C2 training-step time.
@@ -23,7 +23,7 @@ from oracle import mpnn_oracle as O  # noqa: E402
 from tests.conftest import load_gdb13, pretrained_path  # noqa: E402
 
 dev = torch.device("cuda", 0)
-modes = [int(a) for a in sys.argv[1:]] or [0, 4, 64, 128, 192]
+modes = [int(a) for a in sys.argv[1:]] or [0, 4, 64, 256, 128, 192]
 
 
 def ev(fn, K=20, warm=3):
