@@ -42,9 +42,25 @@ CONFIGS = {
     "C4": (dict(max_n_nodes=38, n_node_features=12, len_f_add_per_node=81), 4096, 38, 9, 3,
            "GGNN defaults ZINC-scale synthetic (max_n_nodes=38), batch=4096"),
     "C1": (dict(), 100, 13, 5, 3, "GGNN defaults gdb13 dims, batch=100 (reference plumbing size)"),
+    # profiling configurations of the other model families (not bench lines of BASELINE.json's metric)
+    "C3": (dict(model="AttGGNN", hidden_node_features=256, message_size=256, message_passes=6, max_n_nodes=40,
+                n_node_features=12, len_f_add_per_node=81), 2048, 40, 9, 3,
+           "AttentionGGNN hidden=256, 6 MP steps, batch=2048 synthetic 40-node graphs"),
+    "C5T": (dict(model="EMN"), 1000, 13, 5, 3, "EMN defaults gdb13 dims, batch=1000 (training step of the C5 model)"),
 }
-METRIC = "molecular-graphs/sec (train fwd+bwd) GGNN"
 UNIT = "graphs/s"
+CPU_MICRO_BATCH = 256     # the reference's O(V*E) prologue cannot run the large configurations whole
+
+
+def config_model(cfg):
+    return CONFIGS[cfg][0].get("model", "GGNN")
+
+
+def metric_name(cfg):
+    return f"molecular-graphs/sec (train fwd+bwd) {config_model(cfg)}"
+
+
+METRIC = metric_name("C2")
 
 
 def peaks():
@@ -60,7 +76,8 @@ def make_batch(cfg, seed):
     from graphinvent_b200 import synthetic as S
     from graphinvent_b200.config import make_constants
     kw, B, n_atoms, n_types, n_charges, _ = CONFIGS[cfg]
-    C = make_constants("GGNN", **kw)
+    kw = {k: v for k, v in kw.items() if k != "model"}
+    C = make_constants(config_model(cfg), **kw)
     nodes, edges = S.random_graphs(B, C.max_n_nodes, n_types, n_charges, seed=seed)
     apd = C.max_n_nodes * (C.len_f_add_per_node + C.len_f_conn_per_node) + 1
     target = S.random_targets(B, apd, seed=seed)
@@ -141,6 +158,8 @@ def _pick_cpu_threads(O, C, nodes, edges, target):
 def cpu_train_steps(cfg, steps, warmup, budget_s=None, seed=1002):
     from oracle import mpnn_oracle as O
     C, nodes, edges, target, _ = make_batch(cfg, seed)
+    if cfg not in ("C1", "C2"):      # micro-batch: the dense [V, E] prologue of the reference is quadratic in the batch
+        nodes, edges, target = nodes[:CPU_MICRO_BATCH], edges[:CPU_MICRO_BATCH], target[:CPU_MICRO_BATCH]
     torch.set_num_threads(_pick_cpu_threads(O, C, nodes, edges, target))
     sd = O.init_state_dict(C, seed=0)
     params = [v.clone().requires_grad_(True) for v in sd.values()]
@@ -172,7 +191,7 @@ def run_reference_arm(args):
     total = sum(times)
     value = B * len(times) / total
     cores = torch.get_num_threads()
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+    line = {"impl": "reference", "metric": metric_name(args.config), "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": len(times), "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": CONFIGS[args.config][5], "name": args.config, "step": "fwd+kl_loss+bwd+adam",
@@ -359,7 +378,7 @@ def run_b200_arm(args):
                 "other_classes": {"gemm_nt_ms": pms[0], "gemm_dw_ms": pms[1], "scatter_ms": pms[2],
                                   "gemm_nt_tflops": pwork[0] / pms[0] / 1e9 if pms[0] else 0,
                                   "gemm_dw_tflops": pwork[1] / pms[1] / 1e9 if pms[1] else 0}}
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+    line = {"metric": metric_name(args.config), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": CONFIGS[args.config][5], "name": args.config, "per_gpu_batch": B,
