@@ -68,6 +68,14 @@ int tc_make_map(void* cu_tensor_map, const float* base, int rows, int cols, int 
 extern bool g_use_tc;
 extern int g_tc_debug;
 extern long long* g_tc_timing;
+
+// where a CTA's cycles go, per role (one representative thread each); filled by the TIMING builds of the tcgen05 kernels (gib_tc_timing)
+enum tc_timing_slots {
+  TS_TMA_WAIT_EMPTY = 0, TS_TMA_TOTAL, TS_MMA_WAIT_SPLIT, TS_MMA_WAIT_ACC, TS_MMA_TOTAL, TS_SPL_WAIT_RAW, TS_SPL_WORK,
+  TS_SPL_TOTAL, TS_EPI_WAIT_ACC, TS_EPI_WORK, TS_EPI_TOTAL, TS_KERNEL_TOTAL, TS_ITEMS, TS_KBLOCKS, TS_LAUNCHES,
+  TIMING_SLOTS = 16, TIMING_CTAS = 160
+};
+
 int gemm_dw(const GemmDW& q, cudaStream_t st);
 void gemm_dw_plan(int M, int Nn, int Kk, int* splits, int* chunk);
 void tc_dw_plan(int M, int Nn, int Kk, int* splits, int* chunk);

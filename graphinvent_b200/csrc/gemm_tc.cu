@@ -79,12 +79,6 @@ struct Params {
   long long* timing;
 };
 
-// where a CTA's cycles go, per role (one representative thread each); filled by tc_gemm_nt_kernel<SPLIT, true>
-enum tc_timing_slots {
-  TS_TMA_WAIT_EMPTY = 0, TS_TMA_TOTAL, TS_MMA_WAIT_SPLIT, TS_MMA_WAIT_ACC, TS_MMA_TOTAL, TS_SPL_WAIT_RAW, TS_SPL_WORK,
-  TS_SPL_TOTAL, TS_EPI_WAIT_ACC, TS_EPI_WORK, TS_EPI_TOTAL, TS_KERNEL_TOTAL, TS_ITEMS, TS_KBLOCKS, TS_LAUNCHES,
-  TIMING_SLOTS = 16, TIMING_CTAS = 160
-};
 
 __device__ __forceinline__ long long* timing_row(const Params& P) {
   return P.timing + ((size_t)(P.tn ? TIMING_CTAS : 0) + blockIdx.x) * TIMING_SLOTS;

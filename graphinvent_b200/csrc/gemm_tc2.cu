@@ -107,6 +107,7 @@ struct Params {
   int debug;
   // TN (weight-gradient) mode: problem 0 only; g[0].C = split-K workspace [splits][tn_nn][tn_kk]
   int tn, splits, chunk_rows, tn_rows, tn_nn, tn_kk;
+  long long* timing;   // TIMING build only: same [mode][cta][slot] accumulation table as gemm_tc.cu (gemm.cuh)
 };
 
 struct Item { int p, m0, n0, nkb, z; };   // m0 = first row of the PAIR's 256-row tile
@@ -158,7 +159,21 @@ __device__ __forceinline__ void split_tile(uint8_t* hi_raw, uint8_t* lo_out, int
   }
 }
 
-template <int SPLIT>
+template <bool TIMING>
+__device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, long long& acc) {
+  if constexpr (TIMING) {
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    acc += clock64() - t0;
+  } else {
+    mbar_wait(bar, parity);
+  }
+}
+__device__ __forceinline__ long long* timing_row(const Params& P) {
+  return P.timing + ((size_t)(P.tn ? TIMING_CTAS : 0) + blockIdx.x) * TIMING_SLOTS;
+}
+
+template <int SPLIT, bool TIMING = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc2_gemm_nt_kernel(const __grid_constant__ Maps maps, const Params P) {
   extern __shared__ uint8_t smem_raw[];
@@ -177,6 +192,8 @@ tc2_gemm_nt_kernel(const __grid_constant__ Maps maps, const Params P) {
   const uint32_t rank = cluster_ctarank();         // 0 = leader (issues the MMAs), 1 = peer
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
   const int num_items = P.tn ? P.m_pairs[0] * P.n_tiles[0] * P.splits : P.item_begin[P.nprob];
+  long long t_kernel0 = 0;
+  if constexpr (TIMING) t_kernel0 = clock64();
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -206,12 +223,14 @@ tc2_gemm_nt_kernel(const __grid_constant__ Maps maps, const Params P) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      long long t_wait = 0, t_begin = 0;
+      if constexpr (TIMING) t_begin = clock64();
       for (int item = cluster_id; item < num_items; item += num_clusters) {
         const Item w = decode_item(P, item);
         const int m0 = w.m0 + (int)rank * BM;      // this CTA's accumulator rows
         const int nb0 = w.n0 + (int)rank * BNH;    // this CTA's half of the weight rows
         for (int kb = 0; kb < w.nkb; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_wait_t<TIMING>(&empty[stage], phase ^ 1, t_wait);
           uint8_t* st = smem + stage * STAGE_BYTES;
           if (!P.tn) {
             mbar_arrive_expect_tx(&full_raw[stage], A_BYTES + 2 * BH_BYTES);
@@ -231,6 +250,11 @@ tc2_gemm_nt_kernel(const __grid_constant__ Maps maps, const Params P) {
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
+      if constexpr (TIMING) {
+        long long* T = timing_row(P);
+        T[TS_TMA_WAIT_EMPTY] += t_wait;
+        T[TS_TMA_TOTAL] += clock64() - t_begin;
+      }
     }
   } else if (warp == 1) {
     // ================= MMA issuer (leader CTA only) =================
@@ -238,16 +262,19 @@ tc2_gemm_nt_kernel(const __grid_constant__ Maps maps, const Params P) {
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      long long t_wait_split = 0, t_wait_acc = 0, t_begin = 0, n_kb = 0;
+      if constexpr (TIMING) t_begin = clock64();
       for (int item = cluster_id; item < num_items; item += num_clusters, ++it) {
         const int nkb = decode_item(P, item).nkb;
+        if constexpr (TIMING) n_kb += nkb;
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+        mbar_wait_t<TIMING>(&acc_empty[acc], acc_phase ^ 1, t_wait_acc);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * 2 * BN;   // sum of hi*hi   (same columns in both CTAs' TMEM)
         const uint32_t tmem_x = tmem_d + BN;                // sum of lo*hi + hi*lo
         for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(&full_split[stage], phase);
+          mbar_wait_t<TIMING>(&full_split[stage], phase, t_wait_split);
           tc_fence_after();
           const uint32_t base = smem_u32(smem + stage * STAGE_BYTES);
           uint64_t d_ahi, d_alo, d_bhi, d_blo, kstep;
@@ -274,16 +301,28 @@ tc2_gemm_nt_kernel(const __grid_constant__ Maps maps, const Params P) {
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
+      if constexpr (TIMING) {
+        long long* T = timing_row(P);
+        T[TS_MMA_WAIT_SPLIT] += t_wait_split;
+        T[TS_MMA_WAIT_ACC] += t_wait_acc;
+        T[TS_MMA_TOTAL] += clock64() - t_begin;
+        T[TS_ITEMS] += it;
+        T[TS_KBLOCKS] += n_kb;
+      }
     }
   } else if (warp < 6) {
     // ================= splitters (both CTAs) =================
     const int t = threadIdx.x - 64;   // 0..127
     int stage = 0;
     uint32_t phase = 0;
+    long long t_wait = 0, t_work = 0, t_begin = 0;
+    if constexpr (TIMING) t_begin = clock64();
     for (int item = cluster_id; item < num_items; item += num_clusters) {
       const int nkb = decode_item(P, item).nkb;
       for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(&full_raw[stage], phase);
+        mbar_wait_t<TIMING>(&full_raw[stage], phase, t_wait);
+        long long t_w0 = 0;
+        if constexpr (TIMING) t_w0 = clock64();
         uint8_t* st = smem + stage * STAGE_BYTES;
         if (!(P.debug & 1)) {
           split_tile<SPLIT, A_BYTES>(st, st + A_BYTES, t);
@@ -292,7 +331,16 @@ tc2_gemm_nt_kernel(const __grid_constant__ Maps maps, const Params P) {
         fence_proxy_async();            // this thread's generic-proxy writes -> visible to the tensor-core proxy
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(&full_split[stage], 0);
+        if constexpr (TIMING) t_work += clock64() - t_w0;
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+    if constexpr (TIMING) {
+      if (t == 0) {
+        long long* T = timing_row(P);
+        T[TS_SPL_WAIT_RAW] += t_wait;
+        T[TS_SPL_WORK] += t_work;
+        T[TS_SPL_TOTAL] += clock64() - t_begin;
       }
     }
   } else {
@@ -302,6 +350,8 @@ tc2_gemm_nt_kernel(const __grid_constant__ Maps maps, const Params P) {
     const uint32_t stg_s = smem_u32(smem + STAGES * STAGE_BYTES + BAR_BYTES) + (uint32_t)(warp - 6) * (32 * EPI_LD * 4);
     const int rr = lane >> 2, cc = (lane & 3) * 4;
     int it = 0;
+    long long t_wait = 0, t_work = 0, t_begin = 0;
+    if constexpr (TIMING) t_begin = clock64();
     for (int item = cluster_id; item < num_items; item += num_clusters, ++it) {
       const Item w = decode_item(P, item);
       const GemmNT& g = P.g[w.p];
@@ -311,7 +361,9 @@ tc2_gemm_nt_kernel(const __grid_constant__ Maps maps, const Params P) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int m0 = w.m0 + (int)rank * BM, n0 = w.n0;
-      mbar_wait(&acc_full[acc], acc_phase);
+      mbar_wait_t<TIMING>(&acc_full[acc], acc_phase, t_wait);
+      long long t_w0 = 0;
+      if constexpr (TIMING) t_w0 = clock64();
       tc_fence_after();
 #pragma unroll 1
       for (int chunk = 0; chunk < 4; ++chunk) {
@@ -377,12 +429,28 @@ tc2_gemm_nt_kernel(const __grid_constant__ Maps maps, const Params P) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(&acc_empty[acc], 0);
+      if constexpr (TIMING) t_work += clock64() - t_w0;
+    }
+    if constexpr (TIMING) {
+      if (warp == 6 && lane == 0) {
+        long long* T = timing_row(P);
+        T[TS_EPI_WAIT_ACC] += t_wait;
+        T[TS_EPI_WORK] += t_work;
+        T[TS_EPI_TOTAL] += clock64() - t_begin;
+      }
     }
   }
 
   // nobody leaves while the peer may still signal this CTA's barriers or the pair's MMAs read its shared memory
   tc_fence_before();
   __syncthreads();
+  if constexpr (TIMING) {
+    if (threadIdx.x == 0) {
+      long long* T = timing_row(P);
+      T[TS_KERNEL_TOTAL] += clock64() - t_kernel0;
+      T[TS_LAUNCHES] += 1;
+    }
+  }
   cluster_sync_all();
   if (warp == 1) {
     __syncwarp();
@@ -418,6 +486,8 @@ static int pair_launch(const tc2::Maps& maps, const tc2::Params& P, int items, c
   if (max_clusters == 0) {
     GIB_CUDA_TRY(cudaFuncSetAttribute(tc2_gemm_nt_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     GIB_CUDA_TRY(cudaFuncSetAttribute(tc2_gemm_nt_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    GIB_CUDA_TRY(cudaFuncSetAttribute(tc2_gemm_nt_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    GIB_CUDA_TRY(cudaFuncSetAttribute(tc2_gemm_nt_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     int dev = 0, sms = 0;
     GIB_CUDA_TRY(cudaGetDevice(&dev));
     GIB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -429,8 +499,17 @@ static int pair_launch(const tc2::Maps& maps, const tc2::Params& P, int items, c
   }
   const int clusters = items < max_clusters ? items : max_clusters;
   cfg.gridDim = dim3(2 * clusters, 1, 1);
-  if (g_tc_debug & 64) GIB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc2_gemm_nt_kernel<2>, maps, P));   // raw hi operand
-  else GIB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc2_gemm_nt_kernel<1>, maps, P));
+  tc2::Params Q = P;
+  Q.timing = g_tc_timing;
+  const bool raw_hi = (g_tc_debug & 64) != 0;
+  if (Q.timing) {
+    if (raw_hi) GIB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc2_gemm_nt_kernel<2, true>, maps, Q));
+    else GIB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc2_gemm_nt_kernel<1, true>, maps, Q));
+  } else if (raw_hi) {
+    GIB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc2_gemm_nt_kernel<2>, maps, Q));
+  } else {
+    GIB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc2_gemm_nt_kernel<1>, maps, Q));
+  }
   ++g_launch_count;
   return 0;
 }

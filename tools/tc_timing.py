@@ -2,6 +2,8 @@
 
     python tools/tc_timing.py              # standalone shapes + one full C2 training step
     python tools/tc_timing.py --split2     # same with the SPLIT = 2 build (hi operand = raw tile)
+    python tools/tc_timing.py --mask 128   # any gib_tc_debug mask, e.g. the CTA-pair kernel (its standalone GEMMs go
+                                           # through gib_linear_fwd_tc_planes: the pair kernel needs weight planes)
 
 Per role (one representative thread each) the kernel accumulates clock64 totals: time blocked on each mbarrier and
 time doing its own work.  Printed per mode (NT = forward/dX launches, TN = weight-gradient launches) as a share of
@@ -69,9 +71,10 @@ def ev(fn, K=20, warm=3):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--split2", action="store_true")
+    ap.add_argument("--mask", type=int, default=0)
     args = ap.parse_args()
-    if args.split2:
-        lib.gib_tc_debug(64)
+    mask = args.mask | (64 if args.split2 else 0)
+    lib.gib_tc_debug(mask)
     buf = torch.zeros(2 * CTAS * 16, dtype=torch.int64, device=dev)
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -81,7 +84,13 @@ def main():
         W = torch.randn(N, K, device=dev) / K ** 0.5
         b = torch.randn(N, device=dev)
         Y = torch.empty(M, N, device=dev)
-        call = lambda: check(lib.gib_linear_fwd_tc(P(X), K, P(W), K, P(b), P(Y), N, M, N, K, 1, st), "linear")
+        if mask & 128:
+            hi = ((W.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)                 # cvt.rna.tf32
+            lo = (((W - hi).view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+            call = lambda: check(lib.gib_linear_fwd_tc_planes(P(X), K, P(hi), P(lo), K, P(b), P(Y), N, M, N, K, 1, st),
+                                 "linear")
+        else:
+            call = lambda: check(lib.gib_linear_fwd_tc(P(X), K, P(W), K, P(b), P(Y), N, M, N, K, 1, st), "linear")
         lib.gib_tc_timing(None)
         ms = ev(call)
         ref = torch.nn.functional.selu(X.double() @ W.double().t() + b.double())
