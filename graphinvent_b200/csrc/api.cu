@@ -135,7 +135,7 @@ using namespace gib;
 extern "C" {
 
 const char* gib_last_error(void) { return g_err; }
-int gib_version(void) { return 101; }
+int gib_version(void) { return 102; }   // 102: + adam step, validation NLL, tc timing / planes entry points
 void gib_set_tensor_cores(int on) { g_use_tc = on != 0; }
 int gib_get_tensor_cores(void) { return g_use_tc ? 1 : 0; }
 void gib_tc_debug(int mode) { g_tc_debug = mode; }
