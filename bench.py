@@ -105,9 +105,12 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.monotonic(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """t0, t1 (time.monotonic): the timed region.  nvidia-smi needs a few 100 ms to start streaming, so it is
+        started before the warm-up steps (same load); samples inside [t0, t1] are used when there are any, else every
+        sample taken under load since the start (and `window` says so)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.12)
@@ -116,8 +119,13 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        rows, window = [r for _, r in self.rows], "warm-up + timed region"
+        if t0 is not None and t1 is not None:
+            inside = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.15]
+            if inside:
+                rows, window = inside, "timed region"
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 8:
                 continue
@@ -129,7 +137,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "window": window}
 
 
 # ------------------------------------------------------------------------------------------
@@ -294,25 +302,27 @@ def run_b200_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()               # before the warm-up: nvidia-smi takes a while to start streaming
     for _ in range(max(args.warmup, 3)):
         loss = step(nodes, edges, target)
     barrier()
 
     # ---- timed region 1: device-resident inputs (no instrumentation) ---------------------
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     launches0 = lib.gib_launch_count()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_region0 = time.monotonic()
     ev0.record()
     for _ in range(args.steps):
         loss = step(nodes, edges, target)
     ev1.record()
     barrier()
+    t_region1 = time.monotonic()
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     launches = lib.gib_launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_region0, t_region1) if rank == 0 else None
     final_loss = float(loss.detach())
 
     # ---- timed region 1b: the same K steps with a CUDA-event pair around every GEMM / scatter launch (the live
