@@ -103,6 +103,12 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def wait_first(self, timeout=3.0):
+        """block until nvidia-smi delivered its first sample (it needs 0.1-1 s to start streaming)"""
+        t_end = time.monotonic() + timeout
+        while self.proc is not None and not self.rows and time.monotonic() < t_end:
+            time.sleep(0.02)
+
     def _pump(self):
         for line in self.proc.stdout:
             self.rows.append((time.monotonic(), line.strip()))
@@ -305,6 +311,7 @@ def run_b200_arm(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()               # before the warm-up: nvidia-smi takes a while to start streaming
+        sampler.wait_first()
     for _ in range(max(args.warmup, 3)):
         loss = step(nodes, edges, target)
     barrier()
