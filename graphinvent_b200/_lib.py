@@ -22,12 +22,14 @@ class Dims(ctypes.Structure):
     _fields_ = [(n, c_i) for n in (
         "model", "B", "N", "F", "Ef", "H", "M", "T", "msg_hidden", "msg_depth", "att_hidden", "att_depth",
         "eemb_hidden", "eemb_depth", "gather_width", "gatt_hidden", "gatt_depth", "gemb_hidden", "gemb_depth",
-        "mlp1_hidden", "mlp1_depth", "mlp2_hidden", "mlp2_depth", "f_add", "f_conn")] + [("big", c_f)]
+        "mlp1_hidden", "mlp1_depth", "mlp2_hidden", "mlp2_depth", "f_add", "f_conn")] + [("big", c_f), ("in_dtype", c_i)]
 
 
 MODEL_ID = {"GGNN": 0, "MNN": 1, "AttGGNN": 2, "EMN": 3}
 HDR_INTS = 16
-HDR_E, HDR_P, HDR_TYPE_COUNT, HDR_TYPE_BASE, HDR_FLAGS = 0, 1, 2, 6, 11
+HDR_E, HDR_P, HDR_TYPE_COUNT, HDR_TYPE_BASE, HDR_FLAGS, HDR_CAPACITY = 0, 1, 2, 6, 11, 12
+FLAG_MULTITYPE, FLAG_NONBINARY, FLAG_OVERFLOW = 1, 2, 4
+ABI_VERSION = 200      # must equal gib_version() of the loaded library (include/gib200.h)
 
 _PROTOS = {
     "gib_last_error": (ctypes.c_char_p, []),
@@ -35,9 +37,10 @@ _PROTOS = {
     "gib_set_tensor_cores": (None, [c_i]),
     "gib_get_tensor_cores": (c_i, []),
     "gib_tc_debug": (None, [c_i]),
-    "gib_tc_timing": (None, [c_p]),
+    "gib_device_sm_count": (c_i, []),
     "gib_graph_count_ws_bytes": (c_sz, [c_p]),
     "gib_graph_count": (c_i, [c_p, c_p, c_p, c_p]),
+    "gib_graph_header_capacity": (c_i, [c_p, c_i, c_p, c_p]),
     "gib_graph_bytes": (c_sz, [c_p, c_p]),
     "gib_graph_fill": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p]),
     "gib_graph_array": (c_p, [c_p, c_p, c_p, c_i]),
@@ -52,14 +55,17 @@ _PROTOS = {
     "gib_kl_loss_fwd_bwd": (c_i, [c_p, c_p, c_i, c_i, c_f, c_p, c_p, c_p]),
     "gib_linear_fwd": (c_i, [c_p, c_i, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
     "gib_linear_fwd_tc": (c_i, [c_p, c_i, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
-    "gib_linear_fwd_tc_planes": (c_i, [c_p, c_i, c_p, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
+    "gib_linear_fwd_tc_planes": (c_i, [c_p, c_i, c_p, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p]),
+    "gib_split_planes": (c_i, [c_p, c_p, c_p, c_ll, c_p]),
     "gib_dw_scratch_bytes": (c_sz, [c_i, c_i, c_i]),
-    "gib_linear_bwd_dw": (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_p, c_p, c_i, c_i, c_p, c_p]),
+    "gib_linear_bwd_dw": (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p]),
     "gib_scatter_sum": (c_i, [c_p, c_p, c_i, c_p, c_p, c_p, c_ll, c_p]),
     "gib_seg_softmax": (c_i, [c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_ll, c_p]),
     "gib_gru_gates": (c_i, [c_p, c_p, c_p, c_p, c_i, c_p, c_ll, c_p]),
     "gib_graph_gather": (c_i, [c_p, c_p, c_p, c_p, c_i, c_p, c_i, c_i, c_f, c_p]),
     "gib_validation_nll": (c_i, [c_p, c_p, c_i, c_i, c_p, c_p]),
+    "gib_sum_scaled": (c_i, [c_p, c_i, c_f, c_p, c_p]),
+    "gib_fill_zero": (c_i, [c_p, c_sz, c_p]),
     "gib_adam_step": (c_i, [c_p, c_p, c_p, c_p, c_ll, c_ll, c_d, c_d, c_d, c_d, c_d, c_d, c_p]),
     "gib_sample_actions": (c_i, [c_p, c_i, c_i, c_p, c_p, c_p, c_p]),
     "gib_generation_scratch_bytes": (c_sz, [c_i]),
@@ -79,21 +85,29 @@ def _load():
     path = _build.LIB
     try:
         path = _build.build()
-    except Exception as e:  # stale or missing and no nvcc
+    except Exception as e:  # no nvcc on this box (the GPU box runs the library built in the container)
         if not os.path.exists(path):
             raise ImportError(f"libgib200.so is missing and could not be built: {e}") from e
+        if _build.is_stale():
+            import warnings
+            warnings.warn(f"libgib200.so is older than its sources and could not be rebuilt ({e}); loading it anyway "
+                          "-- the ABI version check below decides")
     lib = ctypes.CDLL(path)
     for name, (res, args) in _PROTOS.items():
         fn = getattr(lib, name)  # AttributeError here == header/library mismatch: fail loudly
         fn.restype = res
         fn.argtypes = args
+    got = lib.gib_version()
+    if got != ABI_VERSION:
+        raise ImportError(f"{path} implements ABI version {got}, this package binds version {ABI_VERSION}: "
+                          "rebuild with `python -m graphinvent_b200.build --force`")
     return lib
 
 
 lib = _load()
 LIB_PATH = _build.LIB
-# diagnosis only: GIB_TC_DEBUG=<mask> selects a tcgen05 GEMM variant for the whole process (include/gib200.h,
-# gib_tc_debug) so that any test or tool can be re-run against it; unset = the product kernels
+# A/B measurements only: GIB_TC_DEBUG=1 routes the dense GEMMs to the first-generation tcgen05 kernel for the whole
+# process (include/gib200.h, gib_tc_debug) so that any test or tool can be re-run against it
 if os.environ.get("GIB_TC_DEBUG"):
     lib.gib_tc_debug(int(os.environ["GIB_TC_DEBUG"], 0))
 

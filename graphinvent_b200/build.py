@@ -34,13 +34,30 @@ def _newest_dep():
     return t
 
 
+def is_stale():
+    return not os.path.exists(LIB) or os.path.getmtime(LIB) < _newest_dep()
+
+
 def build(force=False, verbose=False):
     os.makedirs(LIBDIR, exist_ok=True)
+    if not force and not is_stale():
+        return LIB
+    # every rank of a torchrun job imports the package: serialise concurrent builds of the same tree
+    import fcntl
+    with open(os.path.join(LIBDIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force, verbose):
     objdir = os.path.join(LIBDIR, "obj")
     os.makedirs(objdir, exist_ok=True)
     dep_t = _newest_dep()
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= dep_t:
-        return LIB
+        return LIB          # another process built it while this one waited for the lock
     if not os.path.exists(NVCC):
         raise RuntimeError(f"nvcc not found at {NVCC} and {LIB} is missing or stale")
 
@@ -60,10 +77,12 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=8) as ex:
         objs = list(ex.map(compile_one, sources()))
-    r = subprocess.run([NVCC, "-shared", "-o", LIB, *objs, "-lcudart_static", "-lpthread", "-ldl", "-lrt",
+    tmp = LIB + ".tmp"
+    r = subprocess.run([NVCC, "-shared", "-o", tmp, *objs, "-lcudart_static", "-lpthread", "-ldl", "-lrt",
                         "-L/usr/local/cuda/lib64"], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, LIB)
     return LIB
 
 

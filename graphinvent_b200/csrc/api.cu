@@ -135,28 +135,43 @@ using namespace gib;
 extern "C" {
 
 const char* gib_last_error(void) { return g_err; }
-int gib_version(void) { return 102; }   // 102: + adam step, validation NLL, tc timing / planes entry points
+int gib_version(void) { return 200; }   // 200: capacity mode, int8 inputs, second-generation tcgen05 GEMM, grouped dW
 void gib_set_tensor_cores(int on) { g_use_tc = on != 0; }
 int gib_get_tensor_cores(void) { return g_use_tc ? 1 : 0; }
 void gib_tc_debug(int mode) { g_tc_debug = mode; }
-void gib_tc_timing(long long* device_buf) { g_tc_timing = device_buf; }
+int gib_device_sm_count(void) { return device_sm_count(); }
 
 static int groups_of(const gib_dims* d) { return d->model == GIB_EMN ? 1 : d->Ef; }
+static bool is_cap(const int* hdr) { return hdr[HDR_CAPACITY] != 0; }
 
 size_t gib_graph_count_ws_bytes(const gib_dims* d) {
   return graph_count_ws_ints(d->B, groups_of(d)) * sizeof(int);
 }
-int gib_graph_count(const gib_dims* d, const float* edges, void* count_ws, gib_stream stream) {
-  return graph_count(edges, d->B, d->N, d->Ef, d->model != GIB_EMN, reinterpret_cast<int*>(count_ws), ST(stream));
+int gib_graph_count(const gib_dims* d, const void* edges, void* count_ws, gib_stream stream) {
+  return graph_count(edges, d->in_dtype, d->B, d->N, d->Ef, d->model != GIB_EMN, reinterpret_cast<int*>(count_ws),
+                     ST(stream));
+}
+int gib_graph_header_capacity(const gib_dims* d, int entry_capacity, const void* count_ws, int* hdr) {
+  if (entry_capacity < 1 || !count_ws) { set_error("gib_graph_header_capacity: bad capacity / workspace"); return -1; }
+  const int G = groups_of(d);
+  memset(hdr, 0, HDR_INTS * sizeof(int));
+  hdr[HDR_E] = entry_capacity;
+  // every type group is padded to a multiple of 128 rows: at most 127 pad rows per group
+  hdr[HDR_P] = ceil_div(entry_capacity, kTileRows) * kTileRows + G * kTileRows;
+  hdr[HDR_CAPACITY] = 1;
+  const unsigned long long a = reinterpret_cast<unsigned long long>(count_ws);
+  hdr[HDR_DEV_LO] = (int)(unsigned)(a & 0xffffffffull);
+  hdr[HDR_DEV_HI] = (int)(unsigned)(a >> 32);
+  return 0;
 }
 size_t gib_graph_bytes(const gib_dims* d, const int* hdr) {
   return graph_buf_ints((long long)d->B * d->N, hdr[HDR_E], hdr[HDR_P]) * sizeof(int);
 }
-int gib_graph_fill(const gib_dims* d, const float* edges, const void* count_ws, const int* hdr, void* graph_buf,
+int gib_graph_fill(const gib_dims* d, const void* edges, void* count_ws, const int* hdr, void* graph_buf,
                    gib_stream stream) {
   GraphArrays ga = graph_arrays(graph_buf, (long long)d->B * d->N, hdr[HDR_E], hdr[HDR_P]);
-  return graph_fill(edges, d->B, d->N, d->Ef, d->model != GIB_EMN, reinterpret_cast<const int*>(count_ws), ga,
-                    ST(stream));
+  return graph_fill(edges, d->in_dtype, d->B, d->N, d->Ef, d->model != GIB_EMN, reinterpret_cast<int*>(count_ws), ga,
+                    is_cap(hdr) ? hdr[HDR_E] : 0, is_cap(hdr) ? hdr[HDR_P] : 0, ST(stream));
 }
 void* gib_graph_array(const gib_dims* d, const int* hdr, void* graph_buf, int which) {
   GraphArrays ga = graph_arrays(graph_buf, (long long)d->B * d->N, hdr[HDR_E], hdr[HDR_P]);
@@ -198,7 +213,7 @@ size_t gib_model_workspace_bytes(const gib_dims* d, const int* hdr) {
   if (make_run(*d, hdr, r)) return 0;
   return r.L.total * sizeof(float) + 256;
 }
-int gib_model_forward(const gib_dims* d, const int* hdr, const float* nodes, const float* edges, const void* graph_buf,
+int gib_model_forward(const gib_dims* d, const int* hdr, const void* nodes, const void* edges, const void* graph_buf,
                       const void* packed, void* workspace, float* out, gib_stream stream) {
   Run r;
   GIB_TRY(make_run(*d, hdr, r));
@@ -216,7 +231,7 @@ size_t gib_model_bwd_scratch_bytes(const gib_dims* d, const int* hdr) {
   make_bwd(r, bb);
   return bb.total * sizeof(float) + 256;
 }
-int gib_model_backward(const gib_dims* d, const int* hdr, const float* nodes, const float* edges, const void* graph_buf,
+int gib_model_backward(const gib_dims* d, const int* hdr, const void* nodes, const void* edges, const void* graph_buf,
                        const void* packed, const void* workspace, const float* out, const float* dout,
                        float* const* grads, void* scratch, gib_stream stream) {
   Run r;
@@ -238,6 +253,27 @@ int gib_kl_loss_fwd_bwd(const float* out, const float* target, int B, int apd, f
   if (B <= 0) return 0;
   kl_loss_kernel<<<B, 256, 0, ST(stream)>>>(out, target, apd, grad_scale, loss_rows, dout);
   GIB_LAUNCH_CHECK();
+  return 0;
+}
+
+// out[0] = scale * sum_b rows[b], fixed order (one CTA): the batch-mean of the per-molecule losses without an ATen
+// reduction inside a captured step
+__global__ void __launch_bounds__(256) sum_scaled_kernel(const float* __restrict__ rows, int n, float scale,
+                                                         float* __restrict__ out) {
+  __shared__ float sm[8];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += 256) s += rows[i];
+  s = block_reduce<256>(s, sm, false);
+  if (threadIdx.x == 0) out[0] = s * scale;
+}
+int gib_sum_scaled(const float* rows, int n, float scale, float* out, gib_stream stream) {
+  sum_scaled_kernel<<<1, 256, 0, ST(stream)>>>(rows, n, scale, out);
+  GIB_LAUNCH_CHECK();
+  return 0;
+}
+int gib_fill_zero(void* ptr, size_t bytes, gib_stream stream) {
+  if (bytes == 0) return 0;
+  GIB_CUDA_TRY(cudaMemsetAsync(ptr, 0, bytes, ST(stream)));
   return 0;
 }
 
@@ -271,19 +307,44 @@ int gib_linear_fwd_tc(const float* X, int ldx, const float* W, int ldw, const fl
   return gemm_nt_tc(p, ST(stream));
 }
 int gib_linear_fwd_tc_planes(const float* X, int ldx, const float* W_hi, const float* W_lo, int ldw, const float* bias,
-                             float* Y, int ldy, int M, int N, int K, int act, gib_stream stream) {
+                             float* Y, int ldy, int M, int N, int K, int act, const int* m_dev, const int* base_dev,
+                             gib_stream stream) {
   GemmNT p;
   p.A = X; p.lda = ldx; p.B = W_hi; p.B_hi = W_hi; p.B_lo = W_lo; p.ldb = ldw; p.C = Y; p.ldc = ldy;
   p.M = M; p.N = N; p.K = K; p.bias = bias; p.act = act; p.mode = EPI_ACT; p.n_store = N; p.n_valid = N;
-  return gemm_nt_tc(p, ST(stream));
+  p.m_dev = m_dev; p.base_dev = base_dev;
+  if (g_tc_debug & 1) {
+    if (m_dev) { set_error("device-side row counts need the second-generation kernel"); return -2; }
+    return gemm_nt_tc(p, ST(stream));
+  }
+  return gemm_nt_tc3_group(&p, 1, ST(stream));
+}
+__global__ void split_planes_kernel(const float* __restrict__ W, float* __restrict__ hi, float* __restrict__ lo,
+                                    long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = W[i];
+  unsigned h, l;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(x - __uint_as_float(h)));
+  hi[i] = __uint_as_float(h);
+  lo[i] = __uint_as_float(l);
+}
+int gib_split_planes(const float* W, float* W_hi, float* W_lo, long long n, gib_stream stream) {
+  if (n <= 0) return 0;
+  split_planes_kernel<<<(unsigned)ceil_div_ll(n, 256), 256, 0, ST(stream)>>>(W, W_hi, W_lo, n);
+  GIB_LAUNCH_CHECK();
+  return 0;
 }
 size_t gib_dw_scratch_bytes(int M, int Nn, int Kk) { return gemm_dw_scratch_floats(M, Nn, Kk) * sizeof(float); }
 int gib_linear_bwd_dw(const float* G, int ldg, int Nn, const float* X, int ldx, int Kk, int M, float* dW, float* dbias,
-                      int R, int C, void* scratch, gib_stream stream) {
+                      int R, int C, void* scratch, const int* m_dev, const int* base_dev, gib_stream stream) {
   GemmDW q;
   q.G = G; q.ldg = ldg; q.Nn = Nn; q.X = X; q.ldx = ldx; q.Kk = Kk; q.M = M; q.dW = dW; q.dbias = dbias;
   q.R = R; q.C = C; q.Rb = R; q.Rbp = Nn; q.rs = C; q.cs = 1; q.scratch = reinterpret_cast<float*>(scratch);
   q.half_floats = gemm_dw_half_floats(M, Nn, Kk);
+  q.m_dev = m_dev; q.base_dev = base_dev;
+  GIB_TRY(dw_begin());
   const int rc = gemm_dw(q, ST(stream));
   const int rj = dw_join(ST(stream));
   return rc ? rc : rj;

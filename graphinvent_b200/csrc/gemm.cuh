@@ -28,6 +28,11 @@ struct GemmNT {
   int n_store = 0;
   int n_valid = 0;
   double work = 0;   // algorithmic FLOPs of this launch (0: derive from the padded extents)
+  // Device-side row range (capacity mode, tcgen05 path only): when m_dev is set, A / C / aux point at row 0 of buffers
+  // of M rows (the capacity) and the problem covers rows [*base_dev, *base_dev + *m_dev) of them -- the bond-type
+  // group sizes K0 leaves in device memory, so no launch parameter depends on the batch content.
+  const int* m_dev = nullptr;
+  const int* base_dev = nullptr;
 };
 
 struct GemmTN {  // kernel-level args of the split-K dW kernel
@@ -50,6 +55,17 @@ struct GemmDW {
   float* scratch = nullptr;                           // >= gemm_dw_scratch_floats(...) of the largest call: two halves
   size_t half_floats = 0;                             // size of one half (same value for every call on this scratch)
   double work = 0;                                    // algorithmic FLOPs (0: derive)
+  const int* m_dev = nullptr;                         // device-side row range inside buffers of M rows (see GemmNT)
+  const int* base_dev = nullptr;
+};
+
+// scratch layout of one grouped weight-gradient launch of the second-generation tcgen05 kernel (gemm_tc3.cu)
+struct Dw3Layout {
+  int chunk_rows;            // reduction rows per work item
+  int cap_splits[4];         // split capacity per problem (the live count may be smaller: device-side row counts)
+  size_t part_off[4];        // float offsets of [cap_splits][Nn][Kk] partial products
+  size_t bias_off[4];        // float offsets of [cap_splits][Nn] partial column sums
+  size_t floats;             // total
 };
 
 int gemm_nt(const GemmNT& p, cudaStream_t st);      // dispatches to the tcgen05 path when enabled and eligible
@@ -58,10 +74,14 @@ int gemm_nt_tc(const GemmNT& p, cudaStream_t st);
 int gemm_nt_tc_group(const GemmNT* ps, int n, cudaStream_t st);   // n <= 4 independent problems, one launch
 int gemm_nt_group(const GemmNT* ps, int n, cudaStream_t st);      // dispatcher: grouped tcgen05 launch or per-problem
 bool tc_eligible(const GemmNT& p);
-// CTA-pair candidate (gemm_tc2.cu; gib_tc_debug bit 7): NT problems whose weights come as pre-split hi / lo planes
-bool tc2_eligible(const GemmNT& p);
-int gemm_nt_tc2_group(const GemmNT* ps, int n, cudaStream_t st);
-int gemm_dw_tc2_partials(const GemmDW& q, int* splits_out, cudaStream_t st);   // same contract as gemm_dw_tc_partials
+// second-generation kernel (gemm_tc3.cu): activation operand split in registers and fed through tensor memory
+bool tc3_eligible(const GemmNT& p);
+int gemm_nt_tc3_group(const GemmNT* ps, int n, cudaStream_t st);
+bool tc3_dw_eligible(const GemmDW& q);
+void tc3_dw_layout(const GemmDW* qs, int n, long long plan_rows, Dw3Layout* L);
+int gemm_dw_tc3_partials(const GemmDW* qs, int n, const Dw3Layout& L, float* scratch, cudaStream_t st);
+int gemm_dw_tc3_reduce(const GemmDW* qs, int n, const Dw3Layout& L, const float* scratch, cudaStream_t st);
+int device_sm_count();     // SMs of the current device (cached per device)
 // 2-D fp32 TMA descriptor (CUtensorMap*) with a [box_rows x 32 floats] box; 128-byte swizzle for K-major operand
 // tiles, its 32-byte-atom variant for MN-major ones (weight-gradient mode)
 int tc_make_map(void* cu_tensor_map, const float* base, int rows, int cols, int ld, int box_rows, int mn_major);
@@ -77,6 +97,12 @@ enum tc_timing_slots {
 };
 
 int gemm_dw(const GemmDW& q, cudaStream_t st);
+// n <= 4 weight-gradient problems that may run as ONE grouped tcgen05 launch + ONE reduction launch (siblings of a
+// layer: the per-bond-type message MLPs, the readout heads, the two GRU projections).  plan_rows: expected total
+// reduction rows of the group (0: the sum of q.M), used to size the split so that the group fills the machine once.
+int gemm_dw_group(const GemmDW* qs, int n, long long plan_rows, cudaStream_t st);
+size_t gemm_dw_group_half_floats(const GemmDW* qs, int n, long long plan_rows);
+int dw_begin();            // start of a C-ABI call that uses gemm_dw: forget the previous call's side-stream jobs
 void gemm_dw_plan(int M, int Nn, int Kk, int* splits, int* chunk);
 void tc_dw_plan(int M, int Nn, int Kk, int* splits, int* chunk);
 bool tc_dw_eligible(const GemmDW& q);

@@ -9,6 +9,9 @@
 // dimension that is a multiple of 16 floats, pad columns hold exact zeros, the reduction
 // extent K is a multiple of 16.  Replaces the ATen `addmm`/`mm` call sites of
 // reference gnn/modules.py:162-170 (MLP), gnn/mpnn.py:296 (GRUCell) and their autograd.
+#include <algorithm>
+#include <mutex>
+
 #include "gemm.cuh"
 #include "ops.cuh"
 
@@ -164,9 +167,23 @@ __global__ void __launch_bounds__(256, 2) sgemm_nt_kernel(const GemmNT p) {
     }
 }
 
+// which tensor-core kernel: the second generation (gemm_tc3.cu) unless gib_tc_debug bit 0 asks for the first
+static inline bool use_tc3() { return (g_tc_debug & 1) == 0; }
+
 int gemm_nt(const GemmNT& p, cudaStream_t st) {
-  // tensor-core path for the large GEMMs; small / skinny ones stay on the SIMT kernel
-  if (g_use_tc && p.M >= 1024 && p.N >= 48 && p.K >= 32 && tc_eligible(p)) return gemm_nt_tc(p, st);
+  // tensor-core path for all but the tiny / skinny GEMMs (those stay on the SIMT kernel); a problem whose row count
+  // lives on the device (capacity mode) only exists on the second-generation tensor-core kernel
+  if (p.m_dev) {
+    if (!g_use_tc || !use_tc3() || !tc3_eligible(p)) {
+      set_error("gemm_nt: device-side row counts need the tcgen05 path (tensor cores on, pre-split weights)");
+      return -2;
+    }
+    return gemm_nt_tc3_group(&p, 1, st);
+  }
+  if (g_use_tc && p.N >= 48 && p.K >= 32) {
+    if (use_tc3() && p.M >= 256 && tc3_eligible(p)) return gemm_nt_tc3_group(&p, 1, st);
+    if (p.M >= 1024 && tc_eligible(p)) return gemm_nt_tc(p, st);
+  }
   return gemm_nt_simt(p, st);
 }
 
@@ -174,14 +191,17 @@ int gemm_nt(const GemmNT& p, cudaStream_t st) {
 // together they fill the machine reasonably, else problem by problem.
 int gemm_nt_group(const GemmNT* ps, int n, cudaStream_t st) {
   if (n == 1) return gemm_nt(ps[0], st);
-  bool ok = g_use_tc && n <= 4;
+  bool ok = g_use_tc && n <= 4, ok3 = ok && use_tc3(), dyn = false;
   long long tiles = 0;
   for (int i = 0; i < n && ok; ++i) {
+    if (ps[i].m_dev) dyn = true;
     if (ps[i].M <= 0 || ps[i].N <= 0) continue;
     ok = tc_eligible(ps[i]) && ps[i].K >= 32 && ps[i].N >= 48;
+    ok3 = ok3 && ok && tc3_eligible(ps[i]);
     tiles += (long long)ceil_div(ps[i].M, 128) * ceil_div(ps[i].N, 128);
   }
-  if (ok && tiles >= 16) return gemm_nt_tc_group(ps, n, st);
+  if (ok3 && (tiles >= 4 || dyn)) return gemm_nt_tc3_group(ps, n, st);
+  if (ok && !dyn && tiles >= 16) return gemm_nt_tc_group(ps, n, st);
   for (int i = 0; i < n; ++i) GIB_TRY(gemm_nt(ps[i], st));
   return 0;
 }
@@ -194,10 +214,11 @@ int gemm_nt_simt(const GemmNT& p, cudaStream_t st) {
   }
   ProfScope prof(PROF_GEMM_NT, p.work > 0 ? p.work : 2.0 * p.M * (double)p.N * p.K, st);
   const long long ctas_big = (long long)ceil_div(p.M, 128) * ceil_div(p.N, 128);
-  if (ctas_big >= 148 && p.N > 64) {
+  const int num_sms = device_sm_count();
+  if (ctas_big >= num_sms && p.N > 64) {
     dim3 grid(ceil_div(p.N, 128), ceil_div(p.M, 128));
     sgemm_nt_kernel<128, 128, 2, 2><<<grid, 256, 0, st>>>(p);
-  } else if (p.N <= 64 && (long long)ceil_div(p.M, 128) >= 148) {
+  } else if (p.N <= 64 && (long long)ceil_div(p.M, 128) >= num_sms) {
     dim3 grid(ceil_div(p.N, 64), ceil_div(p.M, 128));
     sgemm_nt_kernel<128, 64, 2, 1><<<grid, 256, 0, st>>>(p);
   } else {
@@ -428,35 +449,59 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(float* __restrict__
 }
 
 // ---- helper side stream ------------------------------------------------------------------------------------
-// The tensor-core GEMM CTAs leave ~8K registers and ~14 KB of shared memory free on every SM, exactly one 256-thread
-// block of the two reduction helpers (32 registers each).  They therefore run on a library-owned side stream,
-// concurrently with the NEXT tensor-core launches of the main stream, instead of serialising ~12 us per layer.
-//   job i (scratch half i&1):  main: [wait done(i-2)] TN partials -> record tn(i)
-//                              side: wait tn(i); column sums of G; fixed-order reduction into the gradients; record done(i)
-//                              main: ... dX GEMM of the layer, TN of the next layer (job i+1), then wait done(i)
-// so at most one job is pending, and it is complete before anything can overwrite the buffers it reads (the G
-// operand's ping/pong partner is only rewritten by the dX GEMM that follows job i+1).  dw_join() drains the side
-// stream into the caller's stream; every C-ABI entry that uses gemm_dw calls it before returning.
-static cudaStream_t g_side = nullptr;
-static cudaEvent_t g_ev_tn[2], g_ev_done[2];
-static bool g_done_valid[2] = {false, false};
-static long long g_dw_calls = 0;
-static int g_pending = -1;        // scratch half of the job whose completion the main stream has not waited for yet
+// A tcgen05 GEMM CTA leaves ~8K registers and some shared memory free on every SM -- room for one 256-thread block
+// of the split reduction.  The reductions therefore run on a library-owned side stream (one per device),
+// concurrently with the NEXT tensor-core launches of the main stream, instead of serialising ~10 us per layer:
+//   job i (scratch half i&1):  main: [wait done(i-2)] partial products (+ bias partials) -> record tn(i)
+//                              side: wait tn(i); fixed-order reduction into the gradients; record done(i)
+// Second-generation kernel: the side job reads only the scratch half (bias column sums come out of the GEMM), so the
+// only hazard is the reuse of that half by job i+2.  First-generation kernel: the side job also reads the G operand
+// (column sums), hence the extra wait before the caller's next dX GEMM (g_pending).  dw_join() drains the side stream
+// into the caller's stream; every C-ABI entry that uses gemm_dw calls dw_begin() first and dw_join() before
+// returning, so the pattern is self-contained per call (fork / join: capturable in a CUDA graph).
+// One thread per device at a time (the C-ABI contract: one host thread drives a device's model).
+struct DwSide {
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_tn[2], ev_done[2];
+  bool done_valid[2] = {false, false};
+  long long calls = 0;
+  int pending = -1;      // first generation: job whose completion the main stream has not waited for yet
+  int last = -1;         // half of the most recent job
+};
+static DwSide g_dw[64];
+static std::mutex g_dw_mu;
 
-static int dw_side_init() {
-  if (g_side) return 0;
-  GIB_CUDA_TRY(cudaStreamCreateWithFlags(&g_side, cudaStreamNonBlocking));
-  for (int i = 0; i < 2; ++i) {
-    GIB_CUDA_TRY(cudaEventCreateWithFlags(&g_ev_tn[i], cudaEventDisableTiming));
-    GIB_CUDA_TRY(cudaEventCreateWithFlags(&g_ev_done[i], cudaEventDisableTiming));
+static int dw_side(DwSide** out) {
+  int dev = 0;
+  GIB_CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) { set_error("device index %d out of range", dev); return -4; }
+  std::lock_guard<std::mutex> lk(g_dw_mu);
+  DwSide& d = g_dw[dev];
+  if (!d.side) {
+    GIB_CUDA_TRY(cudaStreamCreateWithFlags(&d.side, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      GIB_CUDA_TRY(cudaEventCreateWithFlags(&d.ev_tn[i], cudaEventDisableTiming));
+      GIB_CUDA_TRY(cudaEventCreateWithFlags(&d.ev_done[i], cudaEventDisableTiming));
+    }
   }
+  *out = &d;
+  return 0;
+}
+
+int dw_begin() {
+  DwSide* d;
+  GIB_TRY(dw_side(&d));
+  d->done_valid[0] = d->done_valid[1] = false;   // the previous call joined its jobs into its stream
+  d->calls = 0; d->pending = -1; d->last = -1;
   return 0;
 }
 
 int dw_join(cudaStream_t st) {
-  if (g_pending >= 0) {
-    GIB_CUDA_TRY(cudaStreamWaitEvent(st, g_ev_done[g_pending], 0));
-    g_pending = -1;
+  DwSide* d;
+  GIB_TRY(dw_side(&d));
+  if (d->last >= 0) {       // the side stream is in order: the last job's event covers all of them
+    GIB_CUDA_TRY(cudaStreamWaitEvent(st, d->ev_done[d->last], 0));
+    d->last = -1; d->pending = -1;
   }
   return 0;
 }
@@ -466,7 +511,11 @@ size_t gemm_dw_half_floats(int M, int Nn, int Kk) {
   gemm_dw_plan(M, Nn, Kk, &splits, &chunk);
   tc_dw_plan(M, Nn, Kk, &s2, &c2);       // the tensor-core path may pick a different split count
   if (s2 > splits) splits = s2;
-  return (((size_t)splits * Nn * Kk + (size_t)(splits > kColsumSplits ? splits : kColsumSplits) * Nn) + 63) & ~(size_t)63;
+  size_t f = (((size_t)splits * Nn * Kk + (size_t)(splits > kColsumSplits ? splits : kColsumSplits) * Nn) + 63) & ~(size_t)63;
+  GemmDW q; q.M = M; q.Nn = Nn; q.Kk = Kk;
+  Dw3Layout L;
+  tc3_dw_layout(&q, 1, 0, &L);
+  return std::max(f, (L.floats + 63) & ~(size_t)63);
 }
 
 size_t gemm_dw_scratch_floats(int M, int Nn, int Kk) {
@@ -474,9 +523,17 @@ size_t gemm_dw_scratch_floats(int M, int Nn, int Kk) {
   return 2 * gemm_dw_half_floats(M, Nn, Kk);
 }
 
+size_t gemm_dw_group_half_floats(const GemmDW* qs, int n, long long plan_rows) {
+  size_t f = 0;
+  for (int i = 0; i < n; ++i) f = std::max(f, gemm_dw_half_floats(qs[i].M, qs[i].Nn, qs[i].Kk));
+  Dw3Layout L;
+  tc3_dw_layout(qs, n, plan_rows, &L);
+  return std::max(f, (L.floats + 63) & ~(size_t)63);
+}
+
 void gemm_dw_plan(int M, int Nn, int Kk, int* splits, int* chunk) {
   const int tiles = ceil_div(Nn, 128) * ceil_div(Kk, 128);
-  int s = ceil_div(2 * 148, tiles);
+  int s = ceil_div(2 * device_sm_count(), tiles);
   const int max_s = ceil_div(M, 64) > 0 ? ceil_div(M, 64) : 1;  // >= 64 rows per split
   if (s > max_s) s = max_s;
   if (s < 1) s = 1;
@@ -488,37 +545,95 @@ void gemm_dw_plan(int M, int Nn, int Kk, int* splits, int* chunk) {
   *chunk = c;
 }
 
+// grouped weight gradients: one tcgen05 launch (partials + bias partials of every member) on the caller's stream and
+// one fixed-order reduction launch on the side stream; falls back to member-by-member when the group is not eligible
+int gemm_dw_group(const GemmDW* qs, int n, long long plan_rows, cudaStream_t st) {
+  if (n < 1) return 0;
+  if (n > 4) { set_error("gemm_dw_group: %d problems (max 4)", n); return -2; }
+  bool ok = g_use_tc && use_tc3(), dyn = false;
+  long long rows = 0;
+  double work = 0;
+  GemmDW live[4];
+  int nl = 0;
+  for (int i = 0; i < n; ++i) {
+    if (qs[i].m_dev) dyn = true;
+    if (qs[i].M <= 0) continue;
+    if (qs[i].scratch != qs[0].scratch || qs[i].half_floats != qs[0].half_floats) ok = false;
+    if (!tc3_dw_eligible(qs[i]) || qs[i].Nn < 32 || qs[i].Kk < 32) ok = false;
+    rows += qs[i].M;
+    work += qs[i].work > 0 ? qs[i].work : 2.0 * qs[i].M * (double)qs[i].R * qs[i].C;
+    live[nl++] = qs[i];
+  }
+  if (nl == 0) return 0;
+  if (dyn && !ok) {
+    set_error("gemm_dw_group: device-side row counts need the tcgen05 path (tensor cores on, aligned operands)");
+    return -2;
+  }
+  if (!ok || (!dyn && rows < 2048)) {
+    for (int i = 0; i < nl; ++i) GIB_TRY(gemm_dw(live[i], st));
+    return 0;
+  }
+  ProfScope prof(PROF_GEMM_DW, work, st);
+  DwSide* d;
+  GIB_TRY(dw_side(&d));
+  const int half = (int)(d->calls++ & 1);
+  float* const scratch = live[0].scratch + (size_t)half * live[0].half_floats;
+  Dw3Layout L;
+  tc3_dw_layout(live, nl, plan_rows, &L);
+  if (L.floats > live[0].half_floats) {
+    set_error("gemm_dw_group: scratch half of %zu floats is too small for %zu", live[0].half_floats, L.floats);
+    return -2;
+  }
+  if (d->pending >= 0) {      // a first-generation job still reads its G operand: finish it first
+    GIB_CUDA_TRY(cudaStreamWaitEvent(st, d->ev_done[d->pending], 0));
+    d->pending = -1;
+  }
+  if (d->done_valid[half]) GIB_CUDA_TRY(cudaStreamWaitEvent(st, d->ev_done[half], 0));   // job i-2 released this half
+  GIB_TRY(gemm_dw_tc3_partials(live, nl, L, scratch, st));
+  GIB_CUDA_TRY(cudaEventRecord(d->ev_tn[half], st));
+  GIB_CUDA_TRY(cudaStreamWaitEvent(d->side, d->ev_tn[half], 0));
+  GIB_TRY(gemm_dw_tc3_reduce(live, nl, L, scratch, d->side));
+  GIB_CUDA_TRY(cudaEventRecord(d->ev_done[half], d->side));
+  d->done_valid[half] = true;
+  d->last = half;
+  return 0;
+}
+
 int gemm_dw(const GemmDW& q, cudaStream_t st) {
   if (q.M <= 0) return 0;  // nothing to add
   if ((q.ldg & 3) || (q.ldx & 3) || (q.Nn & 3) || (q.Kk & 3)) {
     set_error("gemm_dw: ldg=%d ldx=%d Nn=%d Kk=%d violate the padded-layout contract", q.ldg, q.ldx, q.Nn, q.Kk);
     return -2;
   }
+  if (q.m_dev || (g_use_tc && use_tc3() && q.dW && q.M >= 2048 && q.Nn >= 32 && q.Kk >= 32 && tc3_dw_eligible(q)))
+    return gemm_dw_group(&q, 1, 0, st);
   ProfScope prof(PROF_GEMM_DW, q.work > 0 ? q.work : 2.0 * q.M * (double)q.R * q.C, st);
-  GIB_TRY(dw_side_init());
-  const int half = (int)(g_dw_calls++ & 1);
+  DwSide* d;
+  GIB_TRY(dw_side(&d));
+  const int half = (int)(d->calls++ & 1);
   float* const scratch = q.scratch + (size_t)half * q.half_floats;
-  if (g_done_valid[half]) GIB_CUDA_TRY(cudaStreamWaitEvent(st, g_ev_done[half], 0));   // job i-2 released this half
+  if (d->done_valid[half]) GIB_CUDA_TRY(cudaStreamWaitEvent(st, d->ev_done[half], 0));   // job i-2 released this half
   if (g_use_tc && q.dW && tc_dw_eligible(q)) {
-    // tensor-core partials (tcgen05, MN-major operands straight from the row-major activations) on the main stream;
-    // bias column sums + the fixed-order split reduction on the side stream
+    // first-generation tensor-core partials (MN-major operands straight from the row-major activations) on the main
+    // stream; bias column sums + the fixed-order split reduction on the side stream
     int tsplits = 0;
     GemmDW q2 = q;
     q2.scratch = scratch;
     GIB_TRY(gemm_dw_tc_partials(q2, &tsplits, st));
-    GIB_CUDA_TRY(cudaEventRecord(g_ev_tn[half], st));
-    GIB_CUDA_TRY(cudaStreamWaitEvent(g_side, g_ev_tn[half], 0));
+    GIB_CUDA_TRY(cudaEventRecord(d->ev_tn[half], st));
+    GIB_CUDA_TRY(cudaStreamWaitEvent(d->side, d->ev_tn[half], 0));
     float* part = scratch + (size_t)tsplits * q.Nn * q.Kk;         // [kColsumSplits][Nn] partial column sums
     if (q.dbias) {
-      colsum_partial_kernel<<<kColsumSplits, 256, 0, g_side>>>(part, q.G, q.ldg, q.M, q.Nn);
+      colsum_partial_kernel<<<kColsumSplits, 256, 0, d->side>>>(part, q.G, q.ldg, q.M, q.Nn);
       GIB_LAUNCH_CHECK();
     }
-    GIB_TRY(launch_reduce(scratch, tsplits, q, part, kColsumSplits, g_side));
-    GIB_CUDA_TRY(cudaEventRecord(g_ev_done[half], g_side));
-    g_done_valid[half] = true;
-    const int prev = g_pending;       // the job before this one must be complete before the caller's next dX GEMM
-    g_pending = half;
-    if (prev >= 0 && prev != half) GIB_CUDA_TRY(cudaStreamWaitEvent(st, g_ev_done[prev], 0));
+    GIB_TRY(launch_reduce(scratch, tsplits, q, part, kColsumSplits, d->side));
+    GIB_CUDA_TRY(cudaEventRecord(d->ev_done[half], d->side));
+    d->done_valid[half] = true;
+    const int prev = d->pending;      // the job before this one must be complete before the caller's next dX GEMM
+    d->pending = half;
+    d->last = half;
+    if (prev >= 0 && prev != half) GIB_CUDA_TRY(cudaStreamWaitEvent(st, d->ev_done[prev], 0));
     return 0;
   }
   GIB_TRY(dw_join(st));               // fp32 SIMT path: everything on the caller's stream, nothing left pending

@@ -489,10 +489,7 @@ int tc_make_map(void* map, const float* base, int rows, int cols, int ld, int bo
 }
 
 bool g_use_tc = true;
-int g_tc_debug = 0;               // bit 2 (4): truncation split, bit 4 (16): ignore pre-split weights, bit 6 (64): SPLIT = 2,
-                                  // bit 7 (128): CTA-pair kernel (gemm_tc2.cu) for problems with pre-split weights,
-                                  // bit 8 (256): SPLIT = 3 (explicit LDS / STS)
-long long* g_tc_timing = nullptr; // non-null: launch the TIMING instantiation, per-CTA role timings land here
+int g_tc_debug = 0;               // bit 0: route every GEMM to this first-generation kernel instead of gemm_tc3.cu
 
 bool tc_eligible(const GemmNT& p) {
   return p.M >= 1 && p.N >= 1 && p.K >= 16 && (p.K % 16) == 0 && (p.lda % 4) == 0 && (p.ldb % 4) == 0 &&
@@ -501,53 +498,33 @@ bool tc_eligible(const GemmNT& p) {
 
 static int tc_prepare(int* num_sms_out) {
   using namespace tc;
-  static int num_sms = 0;
-  static bool attr_done = false;
-  if (!attr_done) {
-    int dev = 0;
-    GIB_CUDA_TRY(cudaGetDevice(&dev));
+  static int num_sms_dev[64] = {0};
+  static bool attr_done_dev[64] = {false};
+  int dev = 0;
+  GIB_CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) { set_error("device index %d out of range", dev); return -4; }
+  int& num_sms = num_sms_dev[dev];
+  bool& attr_done = attr_done_dev[dev];
+  if (!attr_done) {   // function attributes are per device
     GIB_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    GIB_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_nt_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     GIB_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_nt_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    GIB_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_nt_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    GIB_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_nt_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    GIB_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_nt_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    GIB_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_nt_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_done = true;
   }
   *num_sms_out = num_sms;
   return 0;
 }
 
-// product: <1> (round-to-nearest split).  Diagnosis builds behind g_tc_debug / g_tc_timing (gib_tc_debug, gib_tc_timing).
+// product instantiation: <1> = round-to-nearest split (the other SPLIT / TIMING template branches are not instantiated)
 static void launch_tc(int grid, const tc::Maps& maps, tc::Params& P, cudaStream_t st) {
   using namespace tc;
-  P.timing = g_tc_timing;
-  const bool split2 = (g_tc_debug & 64) != 0;
-  if (P.timing) {
-    if (split2) tc_gemm_nt_kernel<2, true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps, P);
-    else tc_gemm_nt_kernel<1, true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps, P);
-  } else if (g_tc_debug & 4) {
-    tc_gemm_nt_kernel<0><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps, P);
-  } else if (split2) {
-    tc_gemm_nt_kernel<2><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps, P);
-  } else if (g_tc_debug & 256) {
-    tc_gemm_nt_kernel<3><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps, P);
-  } else {
-    tc_gemm_nt_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps, P);
-  }
+  P.timing = nullptr;
+  tc_gemm_nt_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps, P);
 }
 
 // up to MAXP independent NT problems in one persistent launch
 int gemm_nt_tc_group(const GemmNT* ps, int n, cudaStream_t st) {
   using namespace tc;
   if (n < 1 || n > MAXP) { set_error("gemm_nt_tc_group: %d problems (max %d)", n, MAXP); return -2; }
-  if (g_tc_debug & 128) {           // candidate CTA-pair kernel: whole group or nothing
-    bool all = true;
-    for (int i = 0; i < n; ++i)
-      if (ps[i].M > 0 && ps[i].N > 0 && !tc2_eligible(ps[i])) all = false;
-    if (all) return gemm_nt_tc2_group(ps, n, st);
-  }
   int num_sms = 0;
   GIB_TRY(tc_prepare(&num_sms));
   Maps maps;
@@ -560,7 +537,7 @@ int gemm_nt_tc_group(const GemmNT* ps, int n, cudaStream_t st) {
     if (p.M <= 0 || p.N <= 0) continue;
     if (!tc_eligible(p)) { set_error("gemm_nt_tc: operands violate the TMA alignment contract"); return -2; }
     GIB_TRY(make_map(&maps.a[np], p.A, p.M, p.K, p.lda));
-    const bool presplit = p.B_hi && p.B_lo && !(g_tc_debug & 16) && (reinterpret_cast<uintptr_t>(p.B_hi) & 15) == 0 &&
+    const bool presplit = p.B_hi && p.B_lo && (reinterpret_cast<uintptr_t>(p.B_hi) & 15) == 0 &&
                           (reinterpret_cast<uintptr_t>(p.B_lo) & 15) == 0;
     GIB_TRY(make_map(&maps.b[np], presplit ? p.B_hi : p.B, p.N, p.K, p.ldb));
     if (presplit) GIB_TRY(make_map(&maps.b_lo[np], p.B_lo, p.N, p.K, p.ldb));
@@ -577,7 +554,7 @@ int gemm_nt_tc_group(const GemmNT* ps, int n, cudaStream_t st) {
   if (np == 0) return 0;
   for (int i = np; i <= MAXP; ++i) P.tile_begin[i] = tiles;
   P.nprob = np;
-  P.debug = g_tc_debug;
+  P.debug = 0;
   const int grid = tiles < num_sms ? tiles : num_sms;
   ProfScope prof(PROF_GEMM_NT, work, st);
   launch_tc(grid, maps, P, st);
@@ -590,7 +567,7 @@ int gemm_nt_tc(const GemmNT& p, cudaStream_t st) { return gemm_nt_tc_group(&p, 1
 // ---- weight-gradient GEMM on the tensor cores --------------------------------------------------------------
 void tc_dw_plan(int M, int Nn, int Kk, int* splits, int* chunk) {
   const int tiles = ceil_div(Nn, tc::BM) * ceil_div(Kk, tc::BN);
-  int s = ceil_div(148, tiles);                       // about one work item per SM
+  int s = ceil_div(device_sm_count(), tiles);         // about one work item per SM
   int c = ceil_div(ceil_div(M, s), tc::BKF) * tc::BKF;
   if (c < 8 * tc::BKF) c = 8 * tc::BKF;               // >= 256 reduction rows per item: amortise the 64 KB tile drain
   s = ceil_div(M, c);
@@ -607,7 +584,6 @@ bool tc_dw_eligible(const GemmDW& q) {
 // partial products into q.scratch ([splits][Nn][Kk]); the caller reduces them (reduce_grads_kernel)
 int gemm_dw_tc_partials(const GemmDW& q, int* splits_out, cudaStream_t st) {
   using namespace tc;
-  if (g_tc_debug & 128) return gemm_dw_tc2_partials(q, splits_out, st);   // candidate CTA-pair kernel
   int num_sms = 0;
   GIB_TRY(tc_prepare(&num_sms));
   int splits, chunk;
@@ -625,7 +601,7 @@ int gemm_dw_tc_partials(const GemmDW& q, int* splits_out, cudaStream_t st) {
   P.n_tiles[0] = ceil_div(q.Kk, BN);
   P.nprob = 1;
   P.tn = 1; P.splits = splits; P.chunk_rows = chunk; P.tn_rows = q.M; P.tn_nn = q.Nn; P.tn_kk = q.Kk;
-  P.debug = g_tc_debug;
+  P.debug = 0;
   const int items = P.m_tiles[0] * P.n_tiles[0] * splits;
   const int grid = items < num_sms ? items : num_sms;
   launch_tc(grid, maps, P, st);

@@ -11,11 +11,15 @@ enum : int {
   HDR_TYPE_COUNT = 2,   // [4] entries per bond type
   HDR_TYPE_BASE = 6,    // [5] first row of each type group (multiples of 128); [G] == P
   HDR_FLAGS = 11,
+  HDR_CAPACITY = 12,    // host header only: != 0 -> E / P are capacities, the live header stays on the device ...
+  HDR_DEV_LO = 13,      // ... at this address (low / high 32 bits)
+  HDR_DEV_HI = 14,
   HDR_INTS = 16
 };
 enum : int {
   GRAPH_FLAG_MULTITYPE = 1,  // some (b,i,j) carries more than one non-zero bond type
-  GRAPH_FLAG_NONBINARY = 2   // some non-zero bond value differs from 1
+  GRAPH_FLAG_NONBINARY = 2,  // some non-zero bond value differs from 1
+  GRAPH_FLAG_OVERFLOW = 4    // capacity mode: the batch holds more bond entries than the capacity (results invalid)
 };
 
 struct GraphArrays {
@@ -29,8 +33,11 @@ struct GraphArrays {
 };
 
 size_t graph_count_ws_ints(int B, int G);
-int graph_count(const float* edges, int B, int N, int Ef, int by_type, int* ws, cudaStream_t st);
-int graph_fill(const float* edges, int B, int N, int Ef, int by_type, const int* ws, GraphArrays ga,
-               cudaStream_t st);
+// `edges` is float32 (in_dtype 0) or int8 / uint8 (in_dtype 1: the reference's on-disk format, DataProcesser.py:157-161)
+int graph_count(const void* edges, int in_dtype, int B, int N, int Ef, int by_type, int* ws, cudaStream_t st);
+// cap_E / cap_P > 0: capacity mode -- arrays hold cap_E entries / cap_P rows; writes beyond are dropped, the tail rows
+// [P, cap_P) are padded, and GRAPH_FLAG_OVERFLOW is raised in the device header when the batch does not fit
+int graph_fill(const void* edges, int in_dtype, int B, int N, int Ef, int by_type, int* ws, GraphArrays ga, int cap_E,
+               int cap_P, cudaStream_t st);
 
 }  // namespace gib

@@ -51,17 +51,22 @@ __device__ __forceinline__ int block_exscan(int v, int* sm, int* total) {
 // ---------------------------------------------------------------------------------
 // phase 1a: per-molecule counts
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k0_count_kernel(const float* __restrict__ edges, int B, int N, int Ef,
+// bond values arrive as float32 or as the int8 of the reference's HDF5 files (BlockDatasetLoader.py:139-143 widens
+// them on the host; here K0 reads the bytes directly: 4x less traffic on its dominant operand)
+template <typename T> __device__ __forceinline__ float ld_val(const T* p) { return (float)__ldg(p); }
+
+template <typename T>
+__global__ void __launch_bounds__(128) k0_count_kernel(const T* __restrict__ edges, int B, int N, int Ef,
                                                        int G, int* __restrict__ cnt, int* __restrict__ hdr) {
   __shared__ int sm[8];
   const int b = blockIdx.x;
-  const float* e = edges + (size_t)b * N * N * Ef;
+  const T* e = edges + (size_t)b * N * N * Ef;
   int c[4] = {0, 0, 0, 0};
   int flags = 0;
   for (int cell = threadIdx.x; cell < N * N; cell += 128) {
     int nz = 0;
     for (int t = 0; t < Ef; ++t) {
-      float v = __ldg(e + (size_t)cell * Ef + t);
+      float v = ld_val(e + (size_t)cell * Ef + t);
       if (v != 0.f) {
         ++nz;
         if (G > 1) ++c[t];
@@ -129,10 +134,11 @@ __device__ __forceinline__ int cell_of_src_order(int pos, int N, int G) {
   return (i * N + j) * G + t;
 }
 
-__global__ void __launch_bounds__(256) k0_fill_kernel(const float* __restrict__ edges, int B, int N, int Ef, int G,
+template <typename T>
+__global__ void __launch_bounds__(256) k0_fill_kernel(const T* __restrict__ edges, int B, int N, int Ef, int G,
                                                       const int* __restrict__ cnt, const int* __restrict__ off,
                                                       const int* __restrict__ ent_off, const int* __restrict__ hdr,
-                                                      GraphArrays ga) {
+                                                      GraphArrays ga, int cap_E, int cap_P) {
   extern __shared__ unsigned char smem_raw[];
   const int NN = N * N, cells = NN * G;
   unsigned short* rank_mem = reinterpret_cast<unsigned short*>(smem_raw);
@@ -142,13 +148,13 @@ __global__ void __launch_bounds__(256) k0_fill_kernel(const float* __restrict__ 
   __shared__ int sm[10];
 
   const int b = blockIdx.x;
-  const float* e = edges + (size_t)b * NN * Ef;
+  const T* e = edges + (size_t)b * NN * Ef;
   for (int c = threadIdx.x; c < cells; c += 256) {
     unsigned char f;
-    if (G > 1) f = __ldg(e + c) != 0.f;
+    if (G > 1) f = ld_val(e + c) != 0.f;
     else {
       f = 0;
-      for (int t = 0; t < Ef; ++t) f |= (__ldg(e + (size_t)c * Ef + t) != 0.f);
+      for (int t = 0; t < Ef; ++t) f |= (ld_val(e + (size_t)c * Ef + t) != 0.f);
     }
     flag[c] = f;
   }
@@ -189,25 +195,38 @@ __global__ void __launch_bounds__(256) k0_fill_kernel(const float* __restrict__ 
     if (!flag[c]) continue;
     const int t = c % G, ij = c / G, i = ij / N, j = ij % N;
     const int p = tbase[t] + (int)rank_typ[c] - tstart[t];
-    ga.ent_src[p] = b * N + j;
-    ga.ent_dst[p] = b * N + i;
-    ga.ent_w[p] = (G > 1) ? __ldg(e + c) : 1.f;
-    ga.dst_ent[eoff + rank_mem[c]] = p;
-    ga.src_ent[eoff + rank_src[c]] = p;
+    if (p < cap_P) {                     // capacity mode: an overflowing batch is truncated (and flagged), never
+      ga.ent_src[p] = b * N + j;         // written out of bounds
+      ga.ent_dst[p] = b * N + i;
+      ga.ent_w[p] = (G > 1) ? ld_val(e + c) : 1.f;
+    }
+    const int qd = eoff + rank_mem[c], qs = eoff + rank_src[c];
+    if (qd < cap_E) ga.dst_ent[qd] = p < cap_P ? p : 0;
+    if (qs < cap_E) ga.src_ent[qs] = p < cap_P ? p : 0;
   }
   for (int i = threadIdx.x; i < N; i += 256) {
-    ga.dst_ptr[b * N + i] = eoff + rank_mem[(i * N) * G];           // first cell of row i
-    ga.src_ptr[b * N + i] = eoff + rank_src[(0 * N + i) * G];       // cell (i'=0, j=i, t=0) opens column i
+    ga.dst_ptr[b * N + i] = min(cap_E, eoff + rank_mem[(i * N) * G]);      // first cell of row i
+    ga.src_ptr[b * N + i] = min(cap_E, eoff + rank_src[(0 * N + i) * G]);  // cell (i'=0, j=i, t=0) opens column i
   }
   if (b == B - 1 && threadIdx.x == 0) {
-    ga.dst_ptr[B * N] = eoff + total_b;
-    ga.src_ptr[B * N] = eoff + total_b;
+    ga.dst_ptr[B * N] = min(cap_E, eoff + total_b);
+    ga.src_ptr[B * N] = min(cap_E, eoff + total_b);
   }
 }
 
-__global__ void k0_pad_kernel(const int* __restrict__ hdr, int G, GraphArrays ga) {
+// pad rows of every type group; capacity mode: block G also pads the tail [P, cap_P) and raises the overflow flag
+__global__ void k0_pad_kernel(int* __restrict__ hdr, int G, GraphArrays ga, int cap_E, int cap_P) {
   const int g = blockIdx.x;
-  const int lo = hdr[HDR_TYPE_BASE + g] + hdr[HDR_TYPE_COUNT + g], hi = hdr[HDR_TYPE_BASE + g + 1];
+  int lo, hi;
+  if (g < G) {
+    lo = hdr[HDR_TYPE_BASE + g] + hdr[HDR_TYPE_COUNT + g];
+    hi = hdr[HDR_TYPE_BASE + g + 1];
+  } else {
+    lo = hdr[HDR_P];
+    hi = cap_P;
+    if (threadIdx.x == 0 && (hdr[HDR_E] > cap_E || hdr[HDR_P] > cap_P)) atomicOr(&hdr[HDR_FLAGS], GRAPH_FLAG_OVERFLOW);
+  }
+  hi = min(hi, cap_P);
   for (int p = lo + threadIdx.x; p < hi; p += blockDim.x) {
     ga.ent_src[p] = -1;
     ga.ent_dst[p] = -1;
@@ -217,7 +236,7 @@ __global__ void k0_pad_kernel(const int* __restrict__ hdr, int G, GraphArrays ga
 
 size_t graph_count_ws_ints(int B, int G) { return (size_t)2 * G * B + B + HDR_INTS; }
 
-int graph_count(const float* edges, int B, int N, int Ef, int by_type, int* ws, cudaStream_t st) {
+int graph_count(const void* edges, int in_dtype, int B, int N, int Ef, int by_type, int* ws, cudaStream_t st) {
   const int G = by_type ? Ef : 1;
   if (B <= 0 || N <= 0 || Ef <= 0 || Ef > 4 || (long long)N * N * G > 32768) {
     set_error("graph_count: unsupported dims B=%d N=%d Ef=%d (need Ef<=4, N*N*groups<=32768)", B, N, Ef);
@@ -228,30 +247,41 @@ int graph_count(const float* edges, int B, int N, int Ef, int by_type, int* ws, 
   int* off = cnt + (size_t)G * B;
   int* ent_off = off + (size_t)G * B;
   GIB_CUDA_TRY(cudaMemsetAsync(hdr, 0, HDR_INTS * sizeof(int), st));
-  k0_count_kernel<<<B, 128, 0, st>>>(edges, B, N, Ef, G, cnt, hdr);
+  if (in_dtype == 0)
+    k0_count_kernel<float><<<B, 128, 0, st>>>(reinterpret_cast<const float*>(edges), B, N, Ef, G, cnt, hdr);
+  else
+    k0_count_kernel<signed char><<<B, 128, 0, st>>>(reinterpret_cast<const signed char*>(edges), B, N, Ef, G, cnt, hdr);
   GIB_LAUNCH_CHECK();
   k0_scan_kernel<<<1, 1024, 0, st>>>(B, G, cnt, off, ent_off, hdr);
   GIB_LAUNCH_CHECK();
   return 0;
 }
 
-int graph_fill(const float* edges, int B, int N, int Ef, int by_type, const int* ws, GraphArrays ga,
-               cudaStream_t st) {
+int graph_fill(const void* edges, int in_dtype, int B, int N, int Ef, int by_type, int* ws, GraphArrays ga, int cap_E,
+               int cap_P, cudaStream_t st) {
   const int G = by_type ? Ef : 1;
-  const int* hdr = ws;
+  int* hdr = ws;
   const int* cnt = ws + HDR_INTS;
   const int* off = cnt + (size_t)G * B;
   const int* ent_off = off + (size_t)G * B;
   const int cells = N * N * G;
   const size_t smem = (size_t)3 * (cells + 2) * sizeof(unsigned short) + cells + 16;
-  static size_t smem_allowed = 48 * 1024;   // default dynamic-smem limit; raised on demand (opt-in up to 227 KB)
-  if (smem > smem_allowed) {
-    GIB_CUDA_TRY(cudaFuncSetAttribute(k0_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_allowed = smem;
+  if (smem > 48 * 1024) {   // opt in to more dynamic shared memory (per device and per instantiation; cheap, idempotent)
+    if (in_dtype == 0)
+      GIB_CUDA_TRY(cudaFuncSetAttribute(k0_fill_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else
+      GIB_CUDA_TRY(cudaFuncSetAttribute(k0_fill_kernel<signed char>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
-  k0_fill_kernel<<<B, 256, smem, st>>>(edges, B, N, Ef, G, cnt, off, ent_off, hdr, ga);
+  const bool capm = cap_P > 0;
+  const int cE = capm ? cap_E : 0x7fffffff, cP = capm ? cap_P : 0x7fffffff;
+  if (in_dtype == 0)
+    k0_fill_kernel<float><<<B, 256, smem, st>>>(reinterpret_cast<const float*>(edges), B, N, Ef, G, cnt, off, ent_off,
+                                                 hdr, ga, cE, cP);
+  else
+    k0_fill_kernel<signed char><<<B, 256, smem, st>>>(reinterpret_cast<const signed char*>(edges), B, N, Ef, G, cnt,
+                                                       off, ent_off, hdr, ga, cE, cP);
   GIB_LAUNCH_CHECK();
-  k0_pad_kernel<<<G, 128, 0, st>>>(hdr, G, ga);
+  k0_pad_kernel<<<capm ? G + 1 : G, 128, 0, st>>>(hdr, G, ga, cE, cP);
   GIB_LAUNCH_CHECK();
   return 0;
 }

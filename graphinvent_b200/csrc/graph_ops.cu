@@ -13,23 +13,32 @@ namespace gib {
 // concat2: dst[r, :] = [ a[r, :wa] | b[r, :wb] | 0 ... ]      (dst width = ldd)
 // reference: summation_mpnn.py:121-125 (zero-pad node features), modules.py:46 (cat(hidden, input))
 // ------------------------------------------------------------------------------------
-__global__ void concat2_kernel(float* __restrict__ dst, int ldd, const float* __restrict__ a, int lda, int wa,
-                               const float* __restrict__ b, int ldb, int wb, long long rows) {
+// Either source may be the int8 input tensor of the reference's on-disk format (i8 flags): it is widened here, in the
+// first kernel that touches it, instead of by a host-side cast (BlockDatasetLoader.py:139-143).
+__device__ __forceinline__ float ld_in(const void* p, size_t i, int i8) {
+  return i8 ? (float)__ldg(reinterpret_cast<const signed char*>(p) + i) : __ldg(reinterpret_cast<const float*>(p) + i);
+}
+__global__ void concat2_kernel(float* __restrict__ dst, int ldd, const void* __restrict__ a, int lda, int wa, int a_i8,
+                               const void* __restrict__ b, int ldb, int wb, int b_i8, long long rows) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * ldd) return;
   const long long r = idx / ldd;
   const int c = (int)(idx % ldd);
   float v = 0.f;
-  if (c < wa) v = a[r * lda + c];
-  else if (c < wa + wb) v = b[r * ldb + (c - wa)];
+  if (c < wa) v = ld_in(a, (size_t)r * lda + c, a_i8);
+  else if (c < wa + wb) v = ld_in(b, (size_t)r * ldb + (c - wa), b_i8);
   dst[idx] = v;
+}
+int concat2_in(float* dst, int ldd, const void* a, int lda, int wa, int a_i8, const void* b, int ldb, int wb, int b_i8,
+               long long rows, cudaStream_t st) {
+  if (rows <= 0) return 0;
+  concat2_kernel<<<GIB_1D(rows * ldd, 256), 0, st>>>(dst, ldd, a, lda, wa, a_i8, b, ldb, wb, b_i8, rows);
+  GIB_LAUNCH_CHECK();
+  return 0;
 }
 int concat2(float* dst, int ldd, const float* a, int lda, int wa, const float* b, int ldb, int wb, long long rows,
             cudaStream_t st) {
-  if (rows <= 0) return 0;
-  concat2_kernel<<<GIB_1D(rows * ldd, 256), 0, st>>>(dst, ldd, a, lda, wa, b, ldb, wb, rows);
-  GIB_LAUNCH_CHECK();
-  return 0;
+  return concat2_in(dst, ldd, a, lda, wa, 0, b, ldb, wb, 0, rows, st);
 }
 
 // dst[b, :] = [ flatten_i( f1[b*N + i, :fa] ) | g[b, :W] | 0 ]      (modules.py:257-268)
@@ -544,8 +553,8 @@ int bcast_nodes_add(float* dh, const float* dg, int ld, int N, long long S, cuda
 // group) and in reference order, so entry row == bond index r and dst_ent is the identity.
 // ------------------------------------------------------------------------------------
 // X[r, :] = [ nodes[i, :F] | nodes[j, :F] | edges[i, j, :Ef] | 0 ]
-__global__ void emn_input_kernel(float* __restrict__ X, int ld, const float* __restrict__ nodes,
-                                 const float* __restrict__ edges, const int* __restrict__ ent_dst,
+__global__ void emn_input_kernel(float* __restrict__ X, int ld, const void* __restrict__ nodes,
+                                 const void* __restrict__ edges, int i8, const int* __restrict__ ent_dst,
                                  const int* __restrict__ ent_src, int N, int F, int Ef, long long P) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= P * ld) return;
@@ -554,16 +563,16 @@ __global__ void emn_input_kernel(float* __restrict__ X, int ld, const float* __r
   const int si = __ldg(ent_dst + r), sj = __ldg(ent_src + r);
   float v = 0.f;
   if (si >= 0) {
-    if (c < F) v = nodes[(size_t)si * F + c];
-    else if (c < 2 * F) v = nodes[(size_t)sj * F + (c - F)];
-    else if (c < 2 * F + Ef) v = edges[((size_t)si * N + (sj % N)) * Ef + (c - 2 * F)];
+    if (c < F) v = ld_in(nodes, (size_t)si * F + c, i8);
+    else if (c < 2 * F) v = ld_in(nodes, (size_t)sj * F + (c - F), i8);
+    else if (c < 2 * F + Ef) v = ld_in(edges, ((size_t)si * N + (sj % N)) * Ef + (c - 2 * F), i8);
   }
   X[idx] = v;
 }
-int emn_input(float* X, int ld, const float* nodes, const float* edges, const int* ent_dst, const int* ent_src, int N,
-              int F, int Ef, long long P, cudaStream_t st) {
+int emn_input(float* X, int ld, const void* nodes, const void* edges, int i8, const int* ent_dst, const int* ent_src,
+              int N, int F, int Ef, long long P, cudaStream_t st) {
   if (P <= 0) return 0;
-  emn_input_kernel<<<GIB_1D(P * ld, 256), 0, st>>>(X, ld, nodes, edges, ent_dst, ent_src, N, F, Ef, P);
+  emn_input_kernel<<<GIB_1D(P * ld, 256), 0, st>>>(X, ld, nodes, edges, i8, ent_dst, ent_src, N, F, Ef, P);
   GIB_LAUNCH_CHECK();
   return 0;
 }

@@ -204,16 +204,32 @@ int make_run(const gib_dims& d, const int* hdr, Run& r) {
   r.E = hdr[HDR_E];
   r.P = hdr[HDR_P];
   const int G = d.model == GIB_EMN ? 1 : d.Ef;
-  for (int g = 0; g < 4; ++g) r.tc[g] = g < G ? hdr[HDR_TYPE_COUNT + g] : 0;
-  for (int g = 0; g < 5; ++g) r.tb[g] = g <= G ? hdr[HDR_TYPE_BASE + g] : r.P;
+  r.cap = hdr[HDR_CAPACITY] != 0;
+  r.dev_hdr = nullptr;
+  if (r.cap) {
+    // capacity header (gib_graph_header_capacity): E / P are static capacities, the live counts stay in device memory;
+    // every bond-type group is planned with the whole capacity and located through the device header at run time
+    if (d.model == GIB_EMN) { set_error("capacity mode is implemented for the node-state models (GGNN, MNN, AttentionGGNN)"); return -3; }
+    unsigned long long a = (unsigned)hdr[HDR_DEV_LO] | ((unsigned long long)(unsigned)hdr[HDR_DEV_HI] << 32);
+    r.dev_hdr = reinterpret_cast<const int*>(a);
+    if (!r.dev_hdr) { set_error("capacity header without a device header address"); return -1; }
+    for (int g = 0; g < 4; ++g) r.tc[g] = g < G ? r.P : 0;
+    for (int g = 0; g < 5; ++g) r.tb[g] = 0;
+    r.unit_bonds = false;
+  } else {
+    for (int g = 0; g < 4; ++g) r.tc[g] = g < G ? hdr[HDR_TYPE_COUNT + g] : 0;
+    for (int g = 0; g < 5; ++g) r.tb[g] = g <= G ? hdr[HDR_TYPE_BASE + g] : r.P;
+    r.unit_bonds = (hdr[HDR_FLAGS] & GRAPH_FLAG_NONBINARY) == 0;   // every bond value is exactly 1: skip the w reads
+  }
   r.ngroups = G;
-  r.unit_bonds = (hdr[HDR_FLAGS] & GRAPH_FLAG_NONBINARY) == 0;   // every bond value is exactly 1: skip the w reads
   r.S = (long long)d.B * d.N;
   if (d.B < 1 || r.E < 0 || r.P < r.E) {
     set_error("make_run: inconsistent graph header (B=%d E=%d P=%d)", d.B, r.E, r.P);
     return -1;
   }
-  if ((d.model == GIB_ATTGGNN) && (hdr[HDR_FLAGS] & GRAPH_FLAG_MULTITYPE)) {
+  if (!r.cap && (d.model == GIB_ATTGGNN) && (hdr[HDR_FLAGS] & GRAPH_FLAG_MULTITYPE)) {
+    // (the reference's AggregationMPNN prologue fails on such input as well: aggregation_mpnn.py:115-141 sizes the
+    // neighbour slots by the summed bond VALUES and the index assignment raises a shape mismatch)
     set_error("AttentionGGNN path requires one bond type per bond (a bond with several non-zero types was found)");
     return -3;
   }
@@ -359,11 +375,15 @@ static int mlp_backward(const Run& r, const BwdBufs& bb, const Mlp& m, const flo
 struct MlpJob {
   const Mlp* m; const float* X0; const MlpAct* a; long long row0; int rows;
   float* ext_out; int ext_ld, ext_valid;
+  const int* m_dev = nullptr; const int* base_dev = nullptr;   // capacity mode: live row range on the device
 };
 struct MlpBwdJob {
   const Mlp* m; const float* X0; const MlpAct* a; long long row0; int rows;
   const float* Gtop; float* dX0; int ld_dx; const float* dx_aux;
+  const int* m_dev = nullptr; const int* base_dev = nullptr;
 };
+static const int* type_count_dev(const Run& r, int g) { return r.cap ? r.dev_hdr + HDR_TYPE_COUNT + g : nullptr; }
+static const int* type_base_dev(const Run& r, int g) { return r.cap ? r.dev_hdr + HDR_TYPE_BASE + g : nullptr; }
 
 static size_t mlp_max_ld(const Plan& pl, const Mlp& m) {
   size_t w = 16;
@@ -375,9 +395,11 @@ static int mlp_forward_multi(const Run& r, const MlpJob* jobs, int n) {
   bool same = n <= 4;
   for (int i = 1; i < n && same; ++i) same = jobs[i].m->n == jobs[0].m->n;
   if (!same) {
-    for (int i = 0; i < n; ++i)
+    for (int i = 0; i < n; ++i) {
+      if (jobs[i].m_dev) { set_error("mlp_forward_multi: device-side row counts need MLPs of equal depth"); return -2; }
       GIB_TRY(mlp_forward(r, *jobs[i].m, jobs[i].X0, *jobs[i].a, jobs[i].row0, jobs[i].rows, jobs[i].ext_out,
                           jobs[i].ext_ld, jobs[i].ext_valid));
+    }
     return 0;
   }
   const float* x[4]; int ldx[4];
@@ -397,6 +419,7 @@ static int mlp_forward_multi(const Run& r, const MlpJob* jobs, int n) {
       p.bias = L.pb >= 0 ? r.packed + L.ob : nullptr;
       p.act = j.m->act; p.mode = EPI_ACT;
       p.work = 2.0 * j.rows * (double)L.R * L.C;
+      p.m_dev = j.m_dev; p.base_dev = j.base_dev;
       if (l == j.m->n && j.ext_out) {
         p.C = j.ext_out + (size_t)j.row0 * j.ext_ld; p.ldc = j.ext_ld; p.n_store = j.ext_valid; p.n_valid = j.ext_valid;
       } else {
@@ -411,13 +434,15 @@ static int mlp_forward_multi(const Run& r, const MlpJob* jobs, int n) {
   return 0;
 }
 
-static int mlp_backward_multi(const Run& r, const BwdBufs& bb, const MlpBwdJob* jobs, int n) {
+static int mlp_backward_multi(const Run& r, const BwdBufs& bb, const MlpBwdJob* jobs, int n, long long plan_rows = 0) {
   bool same = n <= 4;
   for (int i = 1; i < n && same; ++i) same = jobs[i].m->n == jobs[0].m->n;
-  if (!same || n == 1) {
-    for (int i = 0; i < n; ++i)
+  if (!same) {
+    for (int i = 0; i < n; ++i) {
+      if (jobs[i].m_dev) { set_error("mlp_backward_multi: device-side row counts need MLPs of equal depth"); return -2; }
       GIB_TRY(mlp_backward(r, bb, *jobs[i].m, jobs[i].X0, *jobs[i].a, jobs[i].row0, jobs[i].rows, jobs[i].Gtop,
                            jobs[i].dX0, jobs[i].ld_dx, jobs[i].dx_aux));
+    }
     return 0;
   }
   const float* G[4]; float* ping[4]; float* pong[4];
@@ -426,11 +451,13 @@ static int mlp_backward_multi(const Run& r, const BwdBufs& bb, const MlpBwdJob* 
     G[i] = jobs[i].Gtop;
     ping[i] = r.scratch + bb.GA + off;
     pong[i] = r.scratch + bb.GB + off;
-    off += ((size_t)std::max(jobs[i].rows, 0) * mlp_max_ld(r.pl, *jobs[i].m) + 31) & ~(size_t)31;
+    // capacity mode: the members' live row ranges are disjoint parts of ONE buffer of `rows` rows -> shared slice
+    if (!jobs[i].m_dev) off += ((size_t)std::max(jobs[i].rows, 0) * mlp_max_ld(r.pl, *jobs[i].m) + 31) & ~(size_t)31;
   }
   for (int l = jobs[0].m->n; l >= 1; --l) {
     GemmNT ps[4];
-    int np = 0, idx[4];
+    GemmDW qs[4];
+    int np = 0, nq = 0, idx[4];
     for (int i = 0; i < n; ++i) {
       const MlpBwdJob& j = jobs[i];
       if (j.rows <= 0) continue;
@@ -438,14 +465,15 @@ static int mlp_backward_multi(const Run& r, const BwdBufs& bb, const MlpBwdJob* 
       const float* Xin = (l == 1) ? j.X0 + (size_t)j.row0 * j.a->ld[0]
                                   : r.ws + j.a->y[l - 1] + (size_t)j.row0 * j.a->ld[l - 1];
       const int ldxin = j.a->ld[l - 1];
-      GemmDW q;
+      GemmDW& q = qs[nq++];
+      q = GemmDW();
       q.G = G[i]; q.ldg = L.Rp; q.Nn = L.Rp; q.X = Xin; q.ldx = ldxin; q.Kk = L.Cp; q.M = j.rows;
       q.dW = r.grads[L.pw] + L.src_off;
       q.dbias = L.pb >= 0 ? r.grads[L.pb] : nullptr;
       q.R = L.R; q.C = L.C; q.Rb = L.Rb; q.Rbp = L.Rbp; q.rs = L.rs; q.cs = L.cs;
       q.scratch = r.scratch + bb.dw; q.half_floats = bb.dw_half;
       q.work = 2.0 * j.rows * (double)L.R * L.C;
-      GIB_TRY(gemm_dw(q, r.st));
+      q.m_dev = j.m_dev; q.base_dev = j.base_dev;
       if (l > 1) {
         GemmNT& p = ps[np];
         p = GemmNT();
@@ -455,14 +483,23 @@ static int mlp_backward_multi(const Run& r, const BwdBufs& bb, const MlpBwdJob* 
         p.work = 2.0 * j.rows * (double)L.R * L.Ct;
         p.C = (G[i] == ping[i]) ? pong[i] : ping[i]; p.ldc = L.Ctp;
         p.mode = EPI_MUL_DACT; p.act = j.m->act; p.aux = Xin; p.ldaux = ldxin;
+        p.m_dev = j.m_dev; p.base_dev = j.base_dev;
         idx[np++] = i;
-      } else if (j.dX0) {   // input gradients may chain through a shared buffer (aux): keep them in order
+      }
+    }
+    GIB_TRY(gemm_dw_group(qs, nq, plan_rows, r.st));   // one grouped launch for the layer's weight gradients
+    if (l == 1) {
+      for (int i = 0; i < n; ++i) {   // input gradients may chain through a shared buffer (aux): keep them in order
+        const MlpBwdJob& j = jobs[i];
+        if (j.rows <= 0 || !j.dX0) continue;
+        const Lin& L = r.pl.lins[j.m->first];
         GemmNT p1;
         p1.A = G[i]; p1.lda = L.Rp; p1.B = r.packed + L.owt; p1.ldb = L.Rp;
         p1.B_hi = r.packed + L.owt_hi; p1.B_lo = r.packed + L.owt_lo;
         p1.M = j.rows; p1.N = L.Ctp; p1.K = L.Rp; p1.n_store = L.Ctp; p1.n_valid = L.Ctp;
         p1.work = 2.0 * j.rows * (double)L.R * L.Ct;
         p1.C = j.dX0; p1.ldc = j.ld_dx;
+        p1.m_dev = j.m_dev; p1.base_dev = j.base_dev;
         if (j.dx_aux) { p1.mode = EPI_ADD; p1.aux = j.dx_aux; p1.ldaux = j.ld_dx; }
         else { p1.mode = EPI_ACT; p1.act = ACT_NONE; p1.bias = nullptr; }
         GIB_TRY(gemm_nt(p1, r.st));
@@ -492,7 +529,7 @@ static int readout_forward(const Run& r, float* out) {
   } else {
     const int ldc = L.gatt.ld[0];
     if (d.model == GIB_EMN) GIB_TRY(concat2(r.ws + L.cat_att, ldc, hT, Hp, d.H, hT, Hp, d.H, S, r.st));
-    else GIB_TRY(concat2(r.ws + L.cat_att, ldc, hT, Hp, d.H, r.nodes, d.F, d.F, S, r.st));  // modules.py:46
+    else GIB_TRY(concat2_in(r.ws + L.cat_att, ldc, hT, Hp, d.H, 0, r.nodes, d.F, d.F, d.in_dtype, S, r.st));  // modules.py:46
     {   // att_nn(cat) and emb_nn(hidden) are independent: one grouped launch per layer
       MlpJob jobs[2] = {{&pl.gatt, r.ws + L.cat_att, &L.gatt, 0, (int)S, nullptr, 0, 0},
                         {&pl.gemb, hT, &L.gemb, 0, (int)S, nullptr, 0, 0}};
@@ -601,7 +638,7 @@ static int node_model_forward(const Run& r, float* out) {
   const Lin& ih = pl.lins[pl.gru_ih];
   const Lin& hh = pl.lins[pl.gru_hh];
   // summation_mpnn.py:121-125: zero-padded node features
-  GIB_TRY(concat2(r.ws + L.h[0], Hp, r.nodes, d.F, d.F, nullptr, 0, 0, S, r.st));
+  GIB_TRY(concat2_in(r.ws + L.h[0], Hp, r.nodes, d.F, d.F, d.in_dtype, nullptr, 0, 0, 0, S, r.st));
   for (int t = 0; t < d.T; ++t) {
     const float* h = r.ws + L.h[t];
     // mpnn.py:286-288 scales the neighbour state by the bond value for GGNN only
@@ -609,11 +646,13 @@ static int node_model_forward(const Run& r, float* out) {
     {   // one grouped launch per layer over the bond types (same input rows layout, per-type weights)
       MlpJob jobs[4];
       for (int g = 0; g < r.ngroups; ++g)
-        jobs[g] = MlpJob{&pl.msg[g], r.ws + L.x0[t], &L.msg[t], r.tb[g], r.tc[g], nullptr, 0, 0};
+        jobs[g] = MlpJob{&pl.msg[g], r.ws + L.x0[t], &L.msg[t], r.tb[g], r.tc[g], nullptr, 0, 0,
+                         type_count_dev(r, g), type_base_dev(r, g)};
       GIB_TRY(mlp_forward_multi(r, jobs, r.ngroups));
       if (d.model == GIB_ATTGGNN) {
         for (int g = 0; g < r.ngroups; ++g)
-          jobs[g] = MlpJob{&pl.att[g], r.ws + L.x0[t], &L.att[t], r.tb[g], r.tc[g], nullptr, 0, 0};
+          jobs[g] = MlpJob{&pl.att[g], r.ws + L.x0[t], &L.att[t], r.tb[g], r.tc[g], nullptr, 0, 0,
+                           type_count_dev(r, g), type_base_dev(r, g)};
         GIB_TRY(mlp_forward_multi(r, jobs, r.ngroups));
       }
     }
@@ -659,15 +698,20 @@ static int node_model_backward(const Run& r, const BwdBufs& bb, const float* out
     const float* h = r.ws + L.h[t];
     GIB_TRY(gru_bwd(sc + bb.dgi, sc + bb.dgh, dh_dir, dh, r.ws + L.gi[t], r.ws + L.gh[t], h, Hp, r.ga.dst_ptr, S,
                     r.st));
-    GemmDW q;
-    q.G = sc + bb.dgi; q.ldg = ih.Rp; q.Nn = ih.Rp; q.X = r.ws + L.msum[t]; q.ldx = Mp; q.Kk = ih.Cp; q.M = (int)S;
-    q.dW = r.grads[ih.pw]; q.dbias = r.grads[ih.pb]; q.R = ih.R; q.C = ih.C; q.Rb = ih.Rb; q.Rbp = ih.Rbp;
-    q.rs = ih.rs; q.cs = ih.cs; q.scratch = sc + bb.dw; q.half_floats = bb.dw_half;
-    GIB_TRY(gemm_dw(q, r.st));
-    q.G = sc + bb.dgh; q.ldg = hh.Rp; q.Nn = hh.Rp; q.X = h; q.ldx = Hp; q.Kk = hh.Cp;
-    q.dW = r.grads[hh.pw]; q.dbias = r.grads[hh.pb]; q.R = hh.R; q.C = hh.C; q.Rb = hh.Rb; q.Rbp = hh.Rbp;
-    q.rs = hh.rs; q.cs = hh.cs;
-    GIB_TRY(gemm_dw(q, r.st));
+    {   // weight gradients of the two GRU projections: one grouped launch
+      GemmDW qs[2];
+      GemmDW& q = qs[0];
+      q.G = sc + bb.dgi; q.ldg = ih.Rp; q.Nn = ih.Rp; q.X = r.ws + L.msum[t]; q.ldx = Mp; q.Kk = ih.Cp; q.M = (int)S;
+      q.dW = r.grads[ih.pw]; q.dbias = r.grads[ih.pb]; q.R = ih.R; q.C = ih.C; q.Rb = ih.Rb; q.Rbp = ih.Rbp;
+      q.rs = ih.rs; q.cs = ih.cs; q.scratch = sc + bb.dw; q.half_floats = bb.dw_half;
+      q.work = 2.0 * S * (double)ih.R * ih.C;
+      qs[1] = q;
+      GemmDW& q2 = qs[1];
+      q2.G = sc + bb.dgh; q2.ldg = hh.Rp; q2.Nn = hh.Rp; q2.X = h; q2.ldx = Hp; q2.Kk = hh.Cp;
+      q2.dW = r.grads[hh.pw]; q2.dbias = r.grads[hh.pb]; q2.R = hh.R; q2.C = hh.C; q2.Rb = hh.Rb; q2.Rbp = hh.Rbp;
+      q2.rs = hh.rs; q2.cs = hh.cs; q2.work = 2.0 * S * (double)hh.R * hh.C;
+      GIB_TRY(gemm_dw_group(qs, 2, 0, r.st));
+    }
     {   // dMsum = dgi W_ih  and  dh[t] = dgh W_hh + direct  (dh[t+1] is dead after gru_bwd): one grouped launch
       GemmNT ps[2];
       GemmNT& p = ps[0];
@@ -703,16 +747,17 @@ static int node_model_backward(const Run& r, const BwdBufs& bb, const float* out
       for (int g = 0; g < r.ngroups; ++g) {
         const size_t ro = (size_t)r.tb[g];
         jobs[g] = MlpBwdJob{&pl.msg[g], r.ws + L.x0[t], &L.msg[t], r.tb[g], r.tc[g], T1 + ro * Mp,
-                            t == 0 ? nullptr : dx0 + ro * Hp, Hp, nullptr};
+                            t == 0 ? nullptr : dx0 + ro * Hp, Hp, nullptr, type_count_dev(r, g), type_base_dev(r, g)};
       }
-      GIB_TRY(mlp_backward_multi(r, bb, jobs, r.ngroups));
+      GIB_TRY(mlp_backward_multi(r, bb, jobs, r.ngroups, r.cap ? r.P : 0));
       if (d.model == GIB_ATTGGNN) {
         for (int g = 0; g < r.ngroups; ++g) {
           const size_t ro = (size_t)r.tb[g];
           jobs[g] = MlpBwdJob{&pl.att[g], r.ws + L.x0[t], &L.att[t], r.tb[g], r.tc[g], T2 + ro * Mp,
-                              t == 0 ? nullptr : dx0 + ro * Hp, Hp, dx0 + ro * Hp};
+                              t == 0 ? nullptr : dx0 + ro * Hp, Hp, dx0 + ro * Hp, type_count_dev(r, g),
+                              type_base_dev(r, g)};
         }
-        GIB_TRY(mlp_backward_multi(r, bb, jobs, r.ngroups));
+        GIB_TRY(mlp_backward_multi(r, bb, jobs, r.ngroups, r.cap ? r.P : 0));
       }
     }
     // dh[t][src] += (w) dX0   -- deterministic gather-reduce over the by-source CSR
@@ -733,8 +778,8 @@ static int emn_forward(const Run& r, float* out) {
   const int Hp = pl.Hp, E = r.E;
   const Lin& ih = pl.lins[pl.gru_ih];
   const Lin& hh = pl.lins[pl.gru_hh];
-  GIB_TRY(emn_input(r.ws + L.xin, L.embnn.ld[0], r.nodes, r.edges, r.ga.ent_dst, r.ga.ent_src, d.N, d.F, d.Ef, E,
-                    r.st));
+  GIB_TRY(emn_input(r.ws + L.xin, L.embnn.ld[0], r.nodes, r.edges, d.in_dtype, r.ga.ent_dst, r.ga.ent_src, d.N, d.F,
+                    d.Ef, E, r.st));
   GIB_TRY(mlp_forward(r, pl.embnn, r.ws + L.xin, L.embnn, 0, E));
   GIB_TRY(tanh_fwd(r.ws + L.xt, r.ws + L.embnn.y[pl.embnn.n], (long long)E * Hp, r.st));      // mpnn.py:469
   GIB_TRY(mlp_forward(r, pl.emsg, r.ws + L.xt, L.emx, 0, E));
@@ -748,6 +793,7 @@ static int emn_forward(const Run& r, float* out) {
                               r.ga.ent_src, r.ga.dst_ptr, E, r.st));
     GemmNT p;
     p.A = r.ws + L.emsg[t]; p.lda = Hp; p.B = r.packed + ih.ow; p.ldb = ih.Cp; p.C = r.ws + L.gi[t]; p.ldc = ih.Rp;
+    p.B_hi = r.packed + ih.ow_hi; p.B_lo = r.packed + ih.ow_lo;
     p.M = E; p.N = ih.Rp; p.K = ih.Cp; p.bias = r.packed + ih.ob; p.act = ACT_NONE; p.mode = EPI_ACT;
     p.n_store = p.n_valid = ih.Rp;
     GIB_TRY(gemm_nt(p, r.st));
@@ -787,6 +833,7 @@ static int emn_backward(const Run& r, const BwdBufs& bb, const float* out, const
     GIB_TRY(colsum_add(r.grads[hh.pb], sc + bb.dgh, hh.Rp, E, hh.R, hh.Rb, hh.Rbp, r.st));  // d b_hh; d W_hh = 0
     GemmNT p;
     p.A = sc + bb.dgi; p.lda = ih.Rp; p.B = r.packed + ih.owt; p.ldb = ih.Rp; p.C = sc + bb.dmsum; p.ldc = Hp;
+    p.B_hi = r.packed + ih.owt_hi; p.B_lo = r.packed + ih.owt_lo;
     p.M = E; p.N = ih.Ctp; p.K = ih.Rp; p.mode = EPI_ACT; p.act = ACT_NONE; p.n_store = p.n_valid = ih.Ctp;
     GIB_TRY(gemm_nt(p, r.st));
     const float* EMm = r.ws + L.emm[t].y[pl.emsg.n];
@@ -819,6 +866,22 @@ static void mlp_extent(const Plan& pl, const Mlp& m, size_t rows, size_t& big, s
     dw = std::max(dw, gemm_dw_scratch_floats((int)rows, L.Rp, L.Cp));
   }
 }
+// the same for sibling MLPs of equal depth whose weight gradients run as one grouped launch per layer
+static void group_extent(const Plan& pl, const Mlp* const* ms, const size_t* rows, int n, long long plan_rows, size_t& dw) {
+  for (int i = 1; i < n; ++i)
+    if (ms[i]->n != ms[0]->n) return;
+  for (int l = 0; l < ms[0]->n; ++l) {
+    GemmDW qs[4];
+    int nq = 0;
+    for (int i = 0; i < n && nq < 4; ++i) {
+      if (rows[i] == 0) continue;
+      const Lin& L = pl.lins[ms[i]->first + l];
+      qs[nq].M = (int)rows[i]; qs[nq].Nn = L.Rp; qs[nq].Kk = L.Cp;
+      ++nq;
+    }
+    if (nq) dw = std::max(dw, 2 * gemm_dw_group_half_floats(qs, nq, plan_rows));
+  }
+}
 
 void make_bwd(const Run& r, BwdBufs& bb) {
   const gib_dims& d = r.pl.d;
@@ -834,6 +897,15 @@ void make_bwd(const Run& r, BwdBufs& bb) {
       if (d.model == GIB_ATTGGNN) mlp_extent(pl, pl.att[g], (size_t)r.tc[g], big, dw);
     }
     big = std::max(big, P * (size_t)std::max(Mp, Hp));
+    {
+      const Mlp* ms[4]; size_t rows[4];
+      for (int g = 0; g < r.ngroups; ++g) { ms[g] = &pl.msg[g]; rows[g] = (size_t)r.tc[g]; }
+      group_extent(pl, ms, rows, r.ngroups, r.cap ? r.P : 0, dw);
+      if (d.model == GIB_ATTGGNN) {
+        for (int g = 0; g < r.ngroups; ++g) ms[g] = &pl.att[g];
+        group_extent(pl, ms, rows, r.ngroups, r.cap ? r.P : 0, dw);
+      }
+    }
   } else {
     mlp_extent(pl, pl.embnn, E, big, dw);
     mlp_extent(pl, pl.emsg, E, big, dw);
@@ -848,13 +920,29 @@ void make_bwd(const Run& r, BwdBufs& bb) {
   mlp_extent(pl, pl.fadd2, B, big, dw);
   mlp_extent(pl, pl.fconn2, B, big, dw);
   mlp_extent(pl, pl.fterm2, B, big, dw);
+  {
+    const Mlp* t2[3] = {&pl.fadd2, &pl.fconn2, &pl.fterm2}; const size_t r2[3] = {B, B, B};
+    group_extent(pl, t2, r2, 3, 0, dw);
+    const Mlp* t1[2] = {&pl.fadd1, &pl.fconn1}; const size_t r1[2] = {S, S};
+    group_extent(pl, t1, r1, 2, 0, dw);
+    if (d.model != GIB_MNN) {
+      const Mlp* ga[2] = {&pl.gemb, &pl.gatt};
+      group_extent(pl, ga, r1, 2, 0, dw);
+    }
+    GemmDW qs[2];
+    qs[0].M = qs[1].M = (int)gru_rows;
+    qs[0].Nn = pl.lins[pl.gru_ih].Rp; qs[0].Kk = pl.lins[pl.gru_ih].Cp;
+    qs[1].Nn = pl.lins[pl.gru_hh].Rp; qs[1].Kk = pl.lins[pl.gru_hh].Cp;
+    dw = std::max(dw, 2 * gemm_dw_group_half_floats(qs, 2, 0));
+  }
   // grouped backward passes keep one ping/pong slice per member inside GA / GB
   {
     size_t types = 64;
     for (int g = 0; g < r.ngroups && d.model != GIB_EMN; ++g) {
       size_t w = mlp_max_ld(pl, pl.msg[g]);
       if (d.model == GIB_ATTGGNN) w = std::max(w, mlp_max_ld(pl, pl.att[g]));
-      types += (size_t)r.tc[g] * w + 32;
+      if (r.cap) types = std::max(types, (size_t)r.P * w + 64);   // capacity mode: the groups share one slice
+      else types += (size_t)r.tc[g] * w + 32;
     }
     big = std::max(big, types);
     big = std::max(big, S * (mlp_max_ld(pl, pl.fadd1) + mlp_max_ld(pl, pl.fconn1)) + 64);
@@ -885,6 +973,7 @@ int model_forward(const Run& r, float* out) {
   return r.pl.d.model == GIB_EMN ? emn_forward(r, out) : node_model_forward(r, out);
 }
 int model_backward(const Run& r, const BwdBufs& bb, const float* out, const float* dout) {
+  GIB_TRY(dw_begin());
   const int rc = r.pl.d.model == GIB_EMN ? emn_backward(r, bb, out, dout) : node_model_backward(r, bb, out, dout);
   const int rj = dw_join(r.st);   // the last reduction job runs on the helper side stream: order it before the caller
   return rc ? rc : rj;

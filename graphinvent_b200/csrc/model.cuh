@@ -72,11 +72,13 @@ struct Run {
   Layout L;
   int E = 0, P = 0, ngroups = 0;
   bool unit_bonds = false;
+  bool cap = false;                 // capacity header: E / P / tc are capacities, live counts are read from dev_hdr
+  const int* dev_hdr = nullptr;     // device copy of the graph header (written by K0)
   const float* w() const { return unit_bonds ? nullptr : ga.ent_w; }
   int tc[4], tb[5];
   long long S = 0;
-  const float* nodes = nullptr;
-  const float* edges = nullptr;
+  const void* nodes = nullptr;     // float32 or int8 (dims.in_dtype)
+  const void* edges = nullptr;
   GraphArrays ga;
   const float* packed = nullptr;
   float* ws = nullptr;          // forward workspace (saved activations)

@@ -16,6 +16,7 @@ struct PackTable { int n; unsigned total_blocks; PackEntry e[kMaxPackEntries]; }
 int pack_all(const PackTable& T, float* packed, cudaStream_t st);
 
 int concat2(float* dst, int ldd, const float* a, int lda, int wa, const float* b, int ldb, int wb, long long rows, cudaStream_t st);
+int concat2_in(float* dst, int ldd, const void* a, int lda, int wa, int a_i8, const void* b, int ldb, int wb, int b_i8, long long rows, cudaStream_t st);
 int concat_flat(float* dst, int ldd, const float* f1, int ldf, int N, int fa, const float* g, int ldg, int W, int B, cudaStream_t st);
 int unflatten_dact(float* G, int ldf, const float* dcat, int ldd, const float* f1, int N, int fa, long long S, cudaStream_t st);
 int dact_slice(float* G, int ldg, const float* dout, const float* out, int ldo, int off, int width, int act, int rows, cudaStream_t st);
@@ -34,7 +35,7 @@ int graph_gather_fwd(float* g, float* att, const float* en, const float* em, int
 int graph_gather_bwd(float* Gen, float* Gem, const float* dg, const float* att, const float* en, const float* em, int ld, int N, int B, cudaStream_t st);
 int sum_nodes_fwd(float* g, const float* h, int ld, int N, int B, cudaStream_t st);
 int bcast_nodes_add(float* dh, const float* dg, int ld, int N, long long S, cudaStream_t st);
-int emn_input(float* X, int ld, const float* nodes, const float* edges, const int* ent_dst, const int* ent_src, int N, int F, int Ef, long long P, cudaStream_t st);
+int emn_input(float* X, int ld, const void* nodes, const void* edges, int i8, const int* ent_dst, const int* ent_src, int N, int F, int Ef, long long P, cudaStream_t st);
 int emn_aggregate_fwd(float* msg, const float* EMx, const float* ENx, const float* EMm, const float* ENm, int ld, const int* ent_dst, const int* ent_src, const int* dst_ptr, long long E, cudaStream_t st);
 int emn_aggregate_bwd(float* dEMx, float* dENx, float* dEMm, float* dENm, float* st3, const float* dmsg, const float* EMx, const float* ENx, const float* EMm, const float* ENm, int ld, const GraphArrays& ga, long long E, cudaStream_t st);
 int mul_dselu(float* G, const float* d, const float* y, long long n, cudaStream_t st);

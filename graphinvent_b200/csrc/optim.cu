@@ -5,6 +5,7 @@
 
 #include "../../include/gib200.h"
 #include "common.cuh"
+#include "gemm.cuh"
 
 namespace gib {
 
@@ -87,7 +88,7 @@ extern "C" int gib_adam_step(float* params, const float* grads, float* exp_avg, 
   if (head > n) head = n;
   const long long work = (n + 3) / 4;
   long long blocks = (work + 255) / 256;
-  const long long cap = 148LL * 6;   // one wave: 6 resident CTAs of 256 threads per SM (40 registers)
+  const long long cap = (long long)gib::device_sm_count() * 6;   // one wave: 6 resident CTAs of 256 threads per SM (40 registers)
   if (blocks > cap) blocks = cap;
   adam_flat_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(params, grads, exp_avg,
                                                                                          exp_avg_sq, n, head, s);

@@ -7,9 +7,10 @@ No computation of the hot path happens in ATen, and there is no CPU path: CPU te
 """
 import ctypes
 
+import numpy as np
 import torch
 
-from ._lib import Dims, HDR_E, HDR_FLAGS, HDR_INTS, HDR_P, MODEL_ID, check, lib
+from ._lib import (Dims, FLAG_MULTITYPE, FLAG_OVERFLOW, HDR_E, HDR_FLAGS, HDR_INTS, HDR_P, MODEL_ID, check, lib)
 
 _u8 = torch.uint8
 
@@ -22,23 +23,36 @@ def _stream(device):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
-def make_dims(model, batch):
+def make_dims(model, batch, in_dtype=0):
+    """`in_dtype`: 0 = float32 batches (BlockDatasetLoader layout), 1 = int8 batches (the on-disk HDF5 type, read
+    directly by K0 and the first-layer kernels)"""
     d = Dims()
     kw = model.dims()
     for name, _ in Dims._fields_:
-        if name in ("model", "B", "big"):
+        if name in ("model", "B", "big", "in_dtype"):
             continue
         setattr(d, name, int(kw.get(name, 0)))
     d.model = MODEL_ID[kw["model"]]
     d.B = int(batch)
     d.big = float(kw.get("big", 1e6))
+    d.in_dtype = int(in_dtype)
     return d
 
 
-def dims_key(model, batch):
+def dims_key(model, batch, in_dtype=0):
     """hashable copy of the `gib_dims` a model would be run with (two models with equal keys can share K0's output)"""
-    d = make_dims(model, batch)
+    d = make_dims(model, batch, in_dtype)
     return tuple(getattr(d, name) for name, _ in Dims._fields_)
+
+
+def input_dtype_code(nodes, edges):
+    """int8 batches stay int8 (K0 / the first-layer kernels widen them on the fly); anything else runs as float32"""
+    return 1 if nodes.dtype == torch.int8 and edges.dtype == torch.int8 else 0
+
+
+def as_input(t, code):
+    t = t.contiguous()
+    return t if (code == 1 and t.dtype == torch.int8) else t.float()
 
 
 def _require_cuda(*tensors):
@@ -93,28 +107,61 @@ def packed_weights(model, d, params):
 class GraphBatch:
     """Device-side bond-entry lists + CSR of one batch (output of K0) and its host header.
     It depends on the batch (B, N, Ef, the edges tensor) and on whether the model is the EMN, not on the weights:
-    two models of one family can share it (`build_graph`, SURVEY.md 8f rank 4: agent + prior of the RL rollout)."""
-    __slots__ = ("hdr", "hdr_np", "buf", "n_entries", "n_rows", "flags", "key", "source")
+    two models of one family can share it (`build_graph`, SURVEY.md 8f rank 4: agent + prior of the RL rollout).
 
-    def __init__(self, d, edges):
+    `capacity=None` (exact mode): one 64-byte device->host read sizes every buffer exactly.
+    `capacity=n` (capacity mode, node-state models): buffers are sized for n bond entries, the live counts stay on the
+    device and the kernels read them there -- no host synchronisation; `overflowed()` / `flags()` read the device
+    header when the caller chooses to (a batch with more entries is truncated and flagged, never written out of
+    bounds).  `buffers=(cws, buf)` re-uses the allocations of an earlier GraphBatch of equal dims and capacity (static
+    addresses: CUDA-graph capture)."""
+    __slots__ = ("hdr", "hdr_np", "buf", "cws", "n_entries", "n_rows", "_flags", "key", "source", "capacity")
+
+    def __init__(self, d, edges, capacity=None, buffers=None):
         dev = edges.device
-        self.key = (d.B, d.N, d.Ef, d.model)
+        self.key = (d.B, d.N, d.Ef, d.model, d.in_dtype)
         self.source = (edges.data_ptr(), edges._version)
+        self.capacity = capacity
         st = _stream(dev)
-        cws = torch.empty(lib.gib_graph_count_ws_bytes(ctypes.byref(d)), dtype=_u8, device=dev)
-        check(lib.gib_graph_count(ctypes.byref(d), _ptr(edges), _ptr(cws), st), "gib_graph_count")
-        # the single device->host read of a forward: 16 ints (the reference syncs twice in nonzero())
-        self.hdr_np = cws[: HDR_INTS * 4].view(torch.int32).cpu().numpy().copy()
+        cws_bytes = lib.gib_graph_count_ws_bytes(ctypes.byref(d))
+        self.cws = buffers[0] if buffers is not None else torch.empty(cws_bytes, dtype=_u8, device=dev)
+        check(lib.gib_graph_count(ctypes.byref(d), _ptr(edges), _ptr(self.cws), st), "gib_graph_count")
+        if capacity is None:
+            # the single device->host read of a forward: 16 ints (the reference syncs twice in nonzero())
+            self.hdr_np = self.cws[: HDR_INTS * 4].view(torch.int32).cpu().numpy().copy()
+            self._flags = int(self.hdr_np[HDR_FLAGS])
+        else:
+            self.hdr_np = np.zeros(HDR_INTS, dtype=np.int32)
+            check(lib.gib_graph_header_capacity(ctypes.byref(d), int(capacity), _ptr(self.cws),
+                                                self.hdr_np.ctypes.data_as(ctypes.c_void_p)),
+                  "gib_graph_header_capacity")
+            self._flags = None
         self.hdr = self.hdr_np.ctypes.data_as(ctypes.c_void_p)
         self.n_entries = int(self.hdr_np[HDR_E])
         self.n_rows = int(self.hdr_np[HDR_P])
-        self.flags = int(self.hdr_np[HDR_FLAGS])
-        self.buf = torch.empty(max(256, lib.gib_graph_bytes(ctypes.byref(d), self.hdr)), dtype=_u8, device=dev)
-        check(lib.gib_graph_fill(ctypes.byref(d), _ptr(edges), _ptr(cws), self.hdr, _ptr(self.buf), st),
+        nbytes = max(256, lib.gib_graph_bytes(ctypes.byref(d), self.hdr))
+        self.buf = buffers[1] if buffers is not None else torch.empty(nbytes, dtype=_u8, device=dev)
+        if self.buf.numel() < nbytes or self.cws.numel() < cws_bytes:
+            raise ValueError("GraphBatch: the supplied buffers are too small for these dims / capacity")
+        check(lib.gib_graph_fill(ctypes.byref(d), _ptr(edges), _ptr(self.cws), self.hdr, _ptr(self.buf), st),
               "gib_graph_fill")
 
+    def device_header(self):
+        """synchronising read of the live 16-int header (capacity mode: counts, flags)"""
+        return self.cws[: HDR_INTS * 4].view(torch.int32).cpu().numpy().copy()
+
+    @property
+    def flags(self):
+        if self._flags is None:
+            return int(self.device_header()[HDR_FLAGS])
+        return self._flags
+
+    def overflowed(self):
+        return bool(self.flags & FLAG_OVERFLOW)
+
     def matches(self, d, edges):
-        return self.key == (d.B, d.N, d.Ef, d.model) and self.source == (edges.data_ptr(), edges._version)
+        return (self.key == (d.B, d.N, d.Ef, d.model, d.in_dtype)
+                and self.source == (edges.data_ptr(), edges._version))
 
     def array(self, d, which, count, dtype=torch.int32):
         """view of one internal array (tests): which = 0 ent_src .. 6 src_ent (include/gib200.h)"""
@@ -128,11 +175,11 @@ class _MPNNFunction(torch.autograd.Function):
     def forward(ctx, model, nodes, edges, *params):
         dev = nodes.device
         B = nodes.shape[0]
-        d = make_dims(model, B)
+        d = make_dims(model, B, input_dtype_code(nodes, edges))
         st = _stream(dev)
         graph = getattr(model, "_graph_in", None)       # a CSR shared between models (mpnn_forward(graph=...))
         if graph is None:
-            graph = GraphBatch(d, edges)
+            graph = GraphBatch(d, edges, capacity=getattr(model, "entry_capacity", None))
         elif not graph.matches(d, edges):
             raise ValueError("the shared GraphBatch was built for another batch, model family or edges tensor")
         packed = packed_weights(model, d, params)
@@ -145,7 +192,7 @@ class _MPNNFunction(torch.autograd.Function):
         check(lib.gib_model_forward(ctypes.byref(d), graph.hdr, _ptr(nodes), _ptr(edges), _ptr(graph.buf),
                                     _ptr(packed), _ptr(ws), _ptr(out), st), "gib_model_forward")
         model.last_stats = {"entries": graph.n_entries, "rows": graph.n_rows, "workspace_bytes": ws_bytes,
-                            "flags": graph.flags}
+                            "flags": graph._flags, "capacity": graph.capacity}
         ctx.model, ctx.d, ctx.graph = model, d, graph
         ctx.save_for_backward(nodes, edges, packed, ws, out)
         ctx.param_meta = [(p.shape, p.numel()) for p in params]
@@ -177,9 +224,10 @@ def build_graph(model, edges):
     `model(nodes, edges, graph=...)`.  `edges` must be the contiguous float32 tensor that is then fed to the models,
     unmodified in between."""
     _require_cuda(edges)
-    if edges.dim() != 4 or edges.dtype != torch.float32 or not edges.is_contiguous():
-        raise ValueError("build_graph expects a contiguous float32 edges tensor [B,N,N,Ef]")
-    return GraphBatch(make_dims(model, edges.shape[0]), edges)
+    if edges.dim() != 4 or edges.dtype not in (torch.float32, torch.int8) or not edges.is_contiguous():
+        raise ValueError("build_graph expects a contiguous float32 (or int8) edges tensor [B,N,N,Ef]")
+    return GraphBatch(make_dims(model, edges.shape[0], 1 if edges.dtype == torch.int8 else 0), edges,
+                      capacity=getattr(model, "entry_capacity", None))
 
 
 def mpnn_forward(model, nodes, edges, graph=None):
@@ -188,8 +236,9 @@ def mpnn_forward(model, nodes, edges, graph=None):
     _require_cuda(*params)
     if nodes.dim() != 3 or edges.dim() != 4:
         raise ValueError("expected nodes [B,N,F] and edges [B,N,N,Ef]")
-    nodes = nodes.contiguous().float()
-    edges = edges.contiguous().float()
+    code = input_dtype_code(nodes, edges)
+    nodes = as_input(nodes, code)
+    edges = as_input(edges, code)
     model._graph_in = graph
     try:
         if torch.is_grad_enabled() and any(p.requires_grad for p in params):

@@ -32,6 +32,9 @@ class _FusedMPNN(torch.nn.Module):
         self._packed_key = None
         self._grad_hook = None      # set by graphinvent_b200.parallel: called on the flat gradient bucket
         self._graph_in = None       # transient: a shared GraphBatch handed to the next forward
+        # None: exact mode (one 64-byte header read per forward).  An int = capacity mode: buffers are sized for that
+        # many bond entries per batch and the forward performs no host synchronisation (functional.GraphBatch)
+        self.entry_capacity = None
         self.last_stats = {}
 
     # dims shared by every model; subclasses add their own fields

@@ -14,10 +14,13 @@
  *    `tensor.data_ptr()`); the library never allocates or frees device memory -- sizes come
  *    from the *_bytes() queries;
  *  - `stream` is a cudaStream_t (`torch.cuda.current_stream().cuda_stream`); every call is
- *    asynchronous on it and performs no host synchronisation;
+ *    asynchronous on it and performs no host synchronisation (the exact-size mode needs ONE 64-byte header read
+ *    by the caller between gib_graph_count and gib_graph_fill; capacity mode needs none);
  *  - return value: 0 ok, < 0 invalid argument (see gib_last_error()), > 0 a cudaError_t;
- *  - nothing is thrown across the boundary; no global mutable state besides the
- *    thread-local error string;
+ *  - nothing is thrown across the boundary.  Library state: the thread-local error string, a per-device helper
+ *    stream for the split reductions (joined back into `stream` before a call returns) and per-device caches of
+ *    function attributes / TMA descriptors (mutex-guarded).  One host thread drives one device's model at a time
+ *    (the reference's threading model); different devices are independent;
  *  - all reductions run in a fixed order (no float atomics): results are bit-stable.
  *
  * Tensor layouts (reference `BlockDatasetLoader.py:135-143`):
@@ -51,17 +54,28 @@ typedef struct gib_dims {
   int mlp1_hidden, mlp1_depth, mlp2_hidden, mlp2_depth;
   int f_add, f_conn;               /* len_f_add_per_node, len_f_conn_per_node */
   float big;                       /* constants.big_positive (1e6) */
+  int in_dtype;                    /* element type of `nodes` / `edges`: 0 = float32 (BlockDatasetLoader.py:139-143),
+                                      1 = int8, the reference's on-disk type (DataProcesser.py:157-161), read
+                                      directly by K0 and the first-layer kernels */
 } gib_dims;
 
-/* Graph header: 16 ints written on the device by gib_graph_count() at the start of its
- * workspace; the caller copies them to the host (the one D2H read of a forward) and passes
- * them back as `hdr_host`.  Index meaning: */
+/* Graph header: 16 ints written on the device by gib_graph_count() at the start of its workspace.
+ * Exact mode: the caller copies them to the host (the one D2H read of a forward) and passes them back as `hdr_host`;
+ * buffers are then sized exactly.  Capacity mode: the caller never reads them -- gib_graph_header_capacity() builds a
+ * host header that carries static capacities and the ADDRESS of the device header, every kernel whose extent depends
+ * on the batch content (the per-bond-type GEMM row ranges, the split counts of the weight-gradient reductions) reads
+ * the live counts from device memory, and no launch parameter depends on the batch: a step has no host
+ * synchronisation and is capturable in a CUDA graph.  Index meaning: */
 enum {
   GIB_HDR_E = 0,          /* bond entries (non-zero elements of `edges`) */
   GIB_HDR_P = 1,          /* rows of the type-grouped entry arrays (groups padded to 128) */
   GIB_HDR_TYPE_COUNT = 2, /* [4] */
   GIB_HDR_TYPE_BASE = 6,  /* [5] */
-  GIB_HDR_FLAGS = 11,     /* bit0: a bond with >1 non-zero type; bit1: a bond value != 1 */
+  GIB_HDR_FLAGS = 11,     /* bit0: a bond with >1 non-zero type; bit1: a bond value != 1; bit2: the batch exceeds the
+                             capacity (capacity mode; results of that step are invalid, nothing is written out of bounds) */
+  GIB_HDR_CAPACITY = 12,  /* host header only: != 0 = capacity header (E, P are capacities) */
+  GIB_HDR_DEV_LO = 13,    /* host header only: address of the device header, low / high 32 bits */
+  GIB_HDR_DEV_HI = 14,
   GIB_HDR_INTS = 16
 };
 
@@ -70,28 +84,22 @@ int gib_version(void);
 /* tcgen05 3xTF32 GEMM path on (default) / off (fp32 SIMT GEMMs only); process-wide switch */
 void gib_set_tensor_cores(int on);
 int gib_get_tensor_cores(void);
-/* diagnosis switches of the tcgen05 GEMM (process-wide, default 0).  Results stay correct with bit2 (truncation
- * split), bit4 (split the weights in the kernel instead of using the packed hi/lo planes) and bit6 (hi operand = raw
- * tile, only the rounded remainder is written); bit7 routes forward/dX GEMMs with packed weights to the CTA-pair
- * candidate kernel (cta_group::2); bit8 = the product arithmetic with explicit shared-window loads / stores;
- * bit0 (skip the split) and bit1 (skip epilogue stores) are timing experiments
- * whose results are wrong. */
+/* bit 0: route the dense GEMMs to the first-generation tcgen05 kernel (operand split through shared memory,
+ * gemm_tc.cu) instead of the default second-generation one (activation operand through tensor memory, gemm_tc3.cu);
+ * process-wide, A/B measurements only.  Capacity mode needs the default. */
 void gib_tc_debug(int mode);
-/* device_buf != NULL: every following tcgen05 GEMM launch runs its TIMING build and ADDS clock64 totals per role
- * into device_buf[mode][cta][16] (int64; mode 0 = forward/dX launches, 1 = weight-gradient launches; 160 CTA rows
- * per mode, i.e. 2 * 160 * 16 * 8 bytes, zeroed by the caller): 0 TMA wait-for-free-stage, 1 TMA loop, 2 MMA
- * wait-for-split-stage, 3 MMA wait-for-free-accumulator, 4 MMA loop, 5 splitter wait-for-TMA, 6 splitter work,
- * 7 splitter loop, 8 epilogue wait-for-accumulator, 9 epilogue work, 10 epilogue loop, 11 whole kernel, 12 work
- * items, 13 k-blocks, 14 launches.  NULL switches back to the product build. */
-void gib_tc_timing(long long* device_buf);
+/* streaming multiprocessors of the current device (grid sizing of the persistent kernels) */
+int gib_device_sm_count(void);
 
 /* ---- K0: edges -> bond entries + CSR.  Replaces summation_mpnn.py:102-118,
  *      aggregation_mpnn.py:105-148, edge_mpnn.py:104-173. ------------------------------- */
 size_t gib_graph_count_ws_bytes(const gib_dims* d);
-int gib_graph_count(const gib_dims* d, const float* edges, void* count_ws, gib_stream stream);
+int gib_graph_count(const gib_dims* d, const void* edges, void* count_ws, gib_stream stream);
+/* capacity mode: host header for `entry_capacity` bond entries (no device access; valid as long as count_ws lives) */
+int gib_graph_header_capacity(const gib_dims* d, int entry_capacity, const void* count_ws, int* hdr_host_out);
 size_t gib_graph_bytes(const gib_dims* d, const int* hdr_host);
-int gib_graph_fill(const gib_dims* d, const float* edges, const void* count_ws, const int* hdr_host,
-                   void* graph_buf, gib_stream stream);
+int gib_graph_fill(const gib_dims* d, const void* edges, void* count_ws, const int* hdr_host, void* graph_buf,
+                   gib_stream stream);
 /* device addresses of the arrays inside graph_buf, for tests / standalone kernel calls:
  * which = 0 ent_src, 1 ent_dst, 2 ent_w, 3 dst_ptr, 4 dst_ent, 5 src_ptr, 6 src_ent */
 void* gib_graph_array(const gib_dims* d, const int* hdr_host, void* graph_buf, int which);
@@ -108,12 +116,12 @@ int gib_model_pack(const gib_dims* d, const float* const* params, void* packed, 
  *      EdgeMPNN.forward (edge_mpnn.py:82-192), the model bodies in mpnn.py and
  *      GraphGather / GlobalReadout (modules.py:39-52, 237-281), and their autograd. ------- */
 size_t gib_model_workspace_bytes(const gib_dims* d, const int* hdr_host);
-int gib_model_forward(const gib_dims* d, const int* hdr_host, const float* nodes, const float* edges,
+int gib_model_forward(const gib_dims* d, const int* hdr_host, const void* nodes, const void* edges,
                       const void* graph_buf, const void* packed, void* workspace, float* out,
                       gib_stream stream);
 size_t gib_model_bwd_scratch_bytes(const gib_dims* d, const int* hdr_host);
 /* grads[i] (same order / shapes as params) are ACCUMULATED into (+=). */
-int gib_model_backward(const gib_dims* d, const int* hdr_host, const float* nodes, const float* edges,
+int gib_model_backward(const gib_dims* d, const int* hdr_host, const void* nodes, const void* edges,
                        const void* graph_buf, const void* packed, const void* workspace,
                        const float* out, const float* dout, float* const* grads, void* scratch,
                        gib_stream stream);
@@ -124,6 +132,11 @@ int gib_model_backward(const gib_dims* d, const int* hdr_host, const float* node
  *      inv_scale); dout = (softmax(out) - t_hat) * grad_scale. ---------------------------- */
 int gib_kl_loss_fwd_bwd(const float* out, const float* target, int B, int apd, float grad_scale,
                         float* loss_rows, float* dout, gib_stream stream);
+
+/* out[0] = scale * sum(rows[0..n)) in a fixed order (the batch mean of loss_rows), and a plain asynchronous memset:
+ * the two non-model operations of a captured training step (graphinvent_b200/graphed.py) */
+int gib_sum_scaled(const float* rows, int n, float scale, float* out, gib_stream stream);
+int gib_fill_zero(void* ptr, size_t bytes, gib_stream stream);
 
 /* ---- validation NLL of the "correct" actions (Analyzer.get_validation_likelihood, Analyzer.py:744-758), one kernel:
  *      nll[b] = -log( sum_k softmax(out[b])_k * target[b,k] / sum_k target[b,k] ).  Rows with an all-zero target
@@ -148,15 +161,18 @@ int gib_linear_fwd(const float* X, int ldx, const float* W, int ldw, const float
 int gib_linear_fwd_tc(const float* X, int ldx, const float* W, int ldw, const float* bias, float* Y, int ldy,
                       int M, int N, int K, int act, gib_stream stream);
 /* the model's own call pattern: W arrives as its TF32 hi / lo planes (hi = rna(W), lo = rna(W - hi), as
- * gib_model_pack lays them out), only X is split in the kernel.  With gib_tc_debug bit 7 this is the entry that
- * reaches the CTA-pair kernel for a single GEMM. */
+ * gib_model_pack lays them out), only X is split in the kernel.  m_dev / base_dev (device ints, may be NULL): the live
+ * row range [*base_dev, *base_dev + *m_dev) inside buffers of M rows (capacity mode). */
 int gib_linear_fwd_tc_planes(const float* X, int ldx, const float* W_hi, const float* W_lo, int ldw,
                              const float* bias, float* Y, int ldy, int M, int N, int K, int act,
-                             gib_stream stream);
+                             const int* m_dev, const int* base_dev, gib_stream stream);
+/* TF32 hi / lo planes of a row-major matrix (round-to-nearest split), for callers of the entry above */
+int gib_split_planes(const float* W, float* W_hi, float* W_lo, long long n, gib_stream stream);
 /* dW[R,C] += G^T X, dbias[R] += colsum(G); G [M, ldg], X [M, ldx]; scratch from gib_dw_scratch_bytes */
 size_t gib_dw_scratch_bytes(int M, int Nn, int Kk);
 int gib_linear_bwd_dw(const float* G, int ldg, int Nn, const float* X, int ldx, int Kk, int M, float* dW,
-                      float* dbias, int R, int C, void* scratch, gib_stream stream);
+                      float* dbias, int R, int C, void* scratch, const int* m_dev, const int* base_dev,
+                      gib_stream stream);
 /* K2 scatter-aggregate: out[s,:] = sum_{q in [ptr[s],ptr[s+1])} w[ent[q]] * msg[ent[q],:]   (w may be NULL) */
 int gib_scatter_sum(float* out, const float* msg, int ld, const int* ptr, const int* ent, const float* w,
                     long long S, gib_stream stream);

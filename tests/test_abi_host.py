@@ -22,8 +22,8 @@ def test_header_symbols_are_exported_and_bound():
     for name in declared:
         assert hasattr(raw, name), f"{name} declared in gib200.h but not exported by libgib200.so"
     assert declared == _lib.exported_symbols()
-    assert _lib.lib.gib_version() >= 100
-    assert ctypes.sizeof(_lib.Dims) == 26 * 4
+    assert _lib.lib.gib_version() == _lib.ABI_VERSION
+    assert ctypes.sizeof(_lib.Dims) == 27 * 4      # 25 ints + big + in_dtype
 
 
 @pytest.mark.parametrize("model", MODELS)
