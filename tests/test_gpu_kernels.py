@@ -147,7 +147,8 @@ def test_linear_bwd_dw(M, N, K):
     dW = torch.ones(N, K, device="cuda")        # accumulate semantics: starts at 1
     db = torch.ones(N, device="cuda")
     sc = torch.empty(lib.gib_dw_scratch_bytes(M, Np, Kp), dtype=torch.uint8, device="cuda")
-    check(lib.gib_linear_bwd_dw(_p(Gp), Np, Np, _p(Xp), Kp, Kp, M, _p(dW), _p(db), N, K, _p(sc), _st()), "dw")
+    check(lib.gib_linear_bwd_dw(_p(Gp), Np, Np, _p(Xp), Kp, Kp, M, _p(dW), _p(db), N, K, _p(sc), None, None, _st()),
+          "dw")
     ref = G.double().t() @ X.double() + 1
     refb = G.double().sum(0) + 1
     # fp32 accumulation of M unit-variance products (entries ~ sqrt(M), max ~ 5 sqrt(M)); the tcgen05 path adds the
@@ -155,6 +156,72 @@ def test_linear_bwd_dw(M, N, K):
     tol = 2e-5 * ref.abs().max().item() + 1e-5
     assert (dW.double() - ref).abs().max().item() <= tol
     assert (db.double() - refb).abs().max().item() <= 2e-5 * refb.abs().max().item() + 1e-4
+
+
+def _planes(lib, check, W):
+    hi, lo = torch.empty_like(W), torch.empty_like(W)
+    check(lib.gib_split_planes(_p(W), _p(hi), _p(lo), W.numel(), _st()), "split_planes")
+    return hi, lo
+
+
+@pytest.mark.parametrize("gen", [2, 1])
+@pytest.mark.parametrize("M,N,K,act", [(128, 128, 32, 0), (100, 48, 16, 1), (1000, 256, 256, 1), (23808, 256, 128, 1),
+                                       (5000, 608, 512, 0), (13312, 256, 144, 1), (1024, 500, 688, 1)])
+def test_tcgen05_linear_planes_both_generations(gen, M, N, K, act):
+    """the model's call pattern: pre-split weight planes, activation split inside the kernel -- second generation
+    (operand through tensor memory) and first generation (through shared memory) against fp64"""
+    Fn, lib, check = _env()
+    torch.manual_seed(M + N + K)
+    X = torch.randn(M, K, device="cuda")
+    W = torch.randn(N, K, device="cuda") / K ** 0.5
+    b = torch.randn(N, device="cuda")
+    hi, lo = _planes(lib, check, W)
+    assert torch.equal((hi.double() + lo.double()).float(), W) or (hi.double() + lo.double() - W.double()).abs().max() < 1e-9
+    Y = torch.full((M, N), float("nan"), device="cuda")
+    lib.gib_tc_debug(1 if gen == 1 else 0)
+    try:
+        check(lib.gib_linear_fwd_tc_planes(_p(X), K, _p(hi), _p(lo), K, _p(b), _p(Y), N, M, N, K, act, None, None,
+                                           _st()), "linear_fwd_tc_planes")
+        torch.cuda.synchronize()
+    finally:
+        lib.gib_tc_debug(0)
+    ref = torch.nn.functional.linear(X.double(), W.double(), b.double())
+    ref = torch.selu(ref) if act else ref
+    assert torch.isfinite(Y).all()
+    assert (Y.double() - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
+
+
+def test_tcgen05_device_side_row_ranges():
+    """capacity mode: the live row range of a problem is read from device memory (K0's bond-type group sizes); rows
+    outside it may hold anything and must stay untouched"""
+    Fn, lib, check = _env()
+    torch.manual_seed(5)
+    cap, N, K = 4096, 256, 256
+    X = torch.randn(cap, K, device="cuda")
+    X[3000:] = float("nan")
+    W = torch.randn(N, K, device="cuda") / K ** 0.5
+    b = torch.randn(N, device="cuda")
+    hi, lo = _planes(lib, check, W)
+    G = torch.randn(cap, N, device="cuda")
+    G[3000:] = float("nan")
+    sc = torch.empty(lib.gib_dw_scratch_bytes(cap, N, K), dtype=torch.uint8, device="cuda")
+    for base, m in [(0, 1000), (128, 2500), (2944, 56), (0, 0)]:
+        md = torch.tensor([m], dtype=torch.int32, device="cuda")
+        bd = torch.tensor([base], dtype=torch.int32, device="cuda")
+        Y = torch.full((cap, N), 7.0, device="cuda")
+        check(lib.gib_linear_fwd_tc_planes(_p(X), K, _p(hi), _p(lo), K, _p(b), _p(Y), N, cap, N, K, 1, _p(md), _p(bd),
+                                           _st()), "linear dyn")
+        ref = torch.selu(torch.nn.functional.linear(X[base:base + m].double(), W.double(), b.double()))
+        if m:
+            assert (Y[base:base + m].double() - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
+        assert (Y[:base] == 7.0).all() and (Y[base + m:] == 7.0).all()
+        dW = torch.zeros(N, K, device="cuda"); db = torch.zeros(N, device="cuda")
+        check(lib.gib_linear_bwd_dw(_p(G), N, N, _p(X), K, K, cap, _p(dW), _p(db), N, K, _p(sc), _p(md), _p(bd),
+                                    _st()), "dw dyn")
+        rw = G[base:base + m].double().t() @ X[base:base + m].double()
+        rb = G[base:base + m].double().sum(0)
+        assert (dW.double() - rw).abs().max().item() <= 2e-5 * rw.abs().max().item() + 1e-5
+        assert (db.double() - rb).abs().max().item() <= 2e-5 * rb.abs().max().item() + 1e-4
 
 
 def _random_csr(S, E, seed):
