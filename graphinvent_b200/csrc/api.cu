@@ -140,6 +140,7 @@ void gib_set_tensor_cores(int on) { g_use_tc = on != 0; }
 int gib_get_tensor_cores(void) { return g_use_tc ? 1 : 0; }
 void gib_tc_debug(int mode) { g_tc_debug = mode; }
 int gib_device_sm_count(void) { return device_sm_count(); }
+void gib_scatter_variant(int v) { g_scatter_variant = v; }
 
 static int groups_of(const gib_dims* d) { return d->model == GIB_EMN ? 1 : d->Ef; }
 static bool is_cap(const int* hdr) { return hdr[HDR_CAPACITY] != 0; }

@@ -661,7 +661,8 @@ static int node_model_forward(const Run& r, float* out) {
       GIB_TRY(seg_softmax_fwd(r.ws + L.msum[t], msgs, r.ws + L.att[t].y[pl.att[0].n], Mp, r.ga.dst_ptr, r.ga.dst_ent,
                               r.w(), S, r.st));
     else
-      GIB_TRY(scatter_sum(r.ws + L.msum[t], msgs, Mp, r.ga.dst_ptr, r.ga.dst_ent, r.w(), 0, S, r.st));
+      GIB_TRY(scatter_sum(r.ws + L.msum[t], msgs, Mp, r.ga.dst_ptr, r.ga.dst_ent, r.w(), 0, S, r.st,
+                          r.cap ? 0.0 : 4.0 * ((double)r.E * d.M + (double)S * d.M + (double)(S + 1))));   // SURVEY.md 8d bytes
     {   // the two GRU input projections are independent: one grouped launch
       GemmNT ps[2];
       GemmNT& p = ps[0];
@@ -763,7 +764,7 @@ static int node_model_backward(const Run& r, const BwdBufs& bb, const float* out
     // dh[t][src] += (w) dX0   -- deterministic gather-reduce over the by-source CSR
     if (t > 0)
       GIB_TRY(scatter_sum(dh, dx0, Hp, r.ga.src_ptr, r.ga.src_ent, d.model == GIB_GGNN ? r.w() : nullptr, 1, S,
-                          r.st));
+                          r.st, r.cap ? 0.0 : 4.0 * ((double)r.E * d.H + 2.0 * S * d.H + (double)(S + 1))));
   }
   return 0;
 }

@@ -24,7 +24,9 @@ int sum3_cols(float* dst, int ldd, int W, const float* a, int lda, int offa, con
 int tanh_fwd(float* y, const float* x, long long n, cudaStream_t st);
 int tanh_selu_bwd(float* G, const float* dy, const float* y, const float* pre, long long n, cudaStream_t st);
 int gather_rows(float* dst, const float* h, int ld, const int* src, const float* w, int scale, long long P, cudaStream_t st);
-int scatter_sum(float* out, const float* msg, int ld, const int* ptr, const int* ent, const float* w, int accumulate, long long S, cudaStream_t st);
+// bytes: algorithmic bytes of the launch for the profile hooks (0 = unknown)
+int scatter_sum(float* out, const float* msg, int ld, const int* ptr, const int* ent, const float* w, int accumulate, long long S, cudaStream_t st, double bytes = 0.0);
+extern int g_scatter_variant;
 int scatter_bwd(float* G, const float* dM, const float* Y, int ld, const int* dst, const float* w, int act, long long P, cudaStream_t st);
 int seg_softmax_fwd(float* out, const float* EM, const float* EN, int ld, const int* ptr, const int* ent, const float* w, long long S, cudaStream_t st);
 int seg_softmax_bwd(float* GM, float* GN, const float* dM, const float* EM, const float* EN, int ld, const int* ptr, const int* ent, const float* w, long long S, cudaStream_t st);

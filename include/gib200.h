@@ -88,6 +88,9 @@ int gib_get_tensor_cores(void);
  * gemm_tc.cu) instead of the default second-generation one (activation operand through tensor memory, gemm_tc3.cu);
  * process-wide, A/B measurements only.  Capacity mode needs the default. */
 void gib_tc_debug(int mode);
+/* K2 scatter-aggregate variant (A/B measurements): bit 0 = two slots per thread, bit 1 = streaming cache hints;
+ * default 3.  Results are identical across variants. */
+void gib_scatter_variant(int v);
 /* streaming multiprocessors of the current device (grid sizing of the persistent kernels) */
 int gib_device_sm_count(void);
 
