@@ -124,6 +124,12 @@ __global__ void __launch_bounds__(256) sample_actions_kernel(const float* __rest
     action[b] = apd - 1;
     lik[b] = expf(o[apd - 1] - mx) / total;
   }
+  // a row with NaN / Inf logits has no owner (every comparison with NaN is false): defined outputs instead of the
+  // caller's uninitialised memory -- "terminate" with a NaN likelihood, which the caller can detect
+  if (threadIdx.x == 0 && !(total == total && total > 0.f && total < INFINITY && target == target)) {
+    action[b] = apd - 1;
+    lik[b] = NAN;
+  }
 }
 
 }  // namespace gib

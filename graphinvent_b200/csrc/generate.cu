@@ -33,7 +33,12 @@ __global__ void gen_decode_kernel(GenDims d, const int* __restrict__ action, con
   const int n = n_nodes[b];
   const int len_add = d.N * d.A * d.CH * d.Ef, len_conn = d.N * d.Ef;
   int kind, bond_to = 0, atom = 0, charge = 0, btype = 0, bond_from = 0, invalid = 0;
-  if (a < len_add) {
+  if (a < 0 || a > len_add + len_conn) {
+    // not an APD index (a corrupted replay trace, or the sampler's NaN fallback): an invalid action that edits
+    // nothing -- the slot terminates as "invalid" and is reset, no field of `rec` is out of range
+    kind = ACT_TERM;
+    invalid = 1;
+  } else if (a < len_add) {
     kind = ACT_ADD;
     btype = a % d.Ef;
     charge = (a / d.Ef) % d.CH;

@@ -66,6 +66,8 @@ class GraphGenerator:
         """replay: optional iterable of (action int32 [B], likelihood float32 [B]) per round (the model is then not
         evaluated); returns the number of finished molecules (may exceed batch_size, as in the reference)."""
         B = self.batch_size
+        if self.rounds or int(self._counters[0].item()):
+            self._allocate()          # a generator object can be used again: start from a fresh batch (:387-423)
         n_generated, rnd = 0, 0
         replay = iter(replay) if replay is not None else None
         st = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
