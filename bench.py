@@ -469,7 +469,7 @@ def run_b200_arm(args):
 
     # ---- kernel classes: an eager pass over the same step with a CUDA-event pair around every GEMM / scatter launch
     launches0 = lib.gib_launch_count()
-    step._enqueue()
+    step._enqueue_all()
     launches_per_step = int(lib.gib_launch_count() - launches0) + 1      # + the Adam launch
     torch.cuda.synchronize()
     prof_steps = max(3, min(args.steps, 20))
@@ -478,7 +478,7 @@ def run_b200_arm(args):
     pv0, pv1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     pv0.record()
     for _ in range(prof_steps):
-        step._enqueue()
+        step._enqueue_all()
     pv1.record()
     barrier()
     ms_instr = max_over_ranks(pv0.elapsed_time(pv1))

@@ -53,6 +53,7 @@ _PROTOS = {
     "gib_model_forward": (c_i, [c_p] * 9),
     "gib_model_bwd_scratch_bytes": (c_sz, [c_p, c_p]),
     "gib_model_backward": (c_i, [c_p] * 12),
+    "gib_model_backward_part": (c_i, [c_p] * 11 + [c_i, c_p]),
     "gib_kl_loss_fwd_bwd": (c_i, [c_p, c_p, c_i, c_i, c_f, c_p, c_p, c_p]),
     "gib_linear_fwd": (c_i, [c_p, c_i, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
     "gib_linear_fwd_tc": (c_i, [c_p, c_i, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),

@@ -241,6 +241,12 @@ size_t gib_model_bwd_scratch_bytes(const gib_dims* d, const int* hdr) {
 int gib_model_backward(const gib_dims* d, const int* hdr, const void* nodes, const void* edges, const void* graph_buf,
                        const void* packed, const void* workspace, const float* out, const float* dout,
                        float* const* grads, void* scratch, gib_stream stream) {
+  return gib_model_backward_part(d, hdr, nodes, edges, graph_buf, packed, workspace, out, dout, grads, scratch, 0,
+                                 stream);
+}
+int gib_model_backward_part(const gib_dims* d, const int* hdr, const void* nodes, const void* edges,
+                            const void* graph_buf, const void* packed, const void* workspace, const float* out,
+                            const float* dout, float* const* grads, void* scratch, int part, gib_stream stream) {
   Run r;
   GIB_TRY(make_run(*d, hdr, r));
   r.nodes = nodes; r.edges = edges;
@@ -252,7 +258,7 @@ int gib_model_backward(const gib_dims* d, const int* hdr, const void* nodes, con
   r.st = ST(stream);
   BwdBufs bb;
   make_bwd(r, bb);
-  return model_backward(r, bb, out, dout);
+  return model_backward(r, bb, out, dout, part);
 }
 
 int gib_kl_loss_fwd_bwd(const float* out, const float* target, int B, int apd, float grad_scale, float* loss_rows,

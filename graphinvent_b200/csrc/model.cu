@@ -683,7 +683,11 @@ static int node_model_forward(const Run& r, float* out) {
   return readout_forward(r, out);
 }
 
-static int node_model_backward(const Run& r, const BwdBufs& bb, const float* out, const float* dout) {
+// part 0: everything; part 1: the readout only (leaves d h_final in scratch[bb.dh]; the gradients of the gather /
+// APDReadout parameters -- the tail of the gradient bucket, 79 % of it -- are final afterwards); part 2: the message
+// passes only (continues from scratch[bb.dh]).  Splitting lets a data-parallel caller start the all-reduce of the
+// readout gradients while the message-passing backward still runs.
+static int node_model_backward(const Run& r, const BwdBufs& bb, const float* out, const float* dout, int part) {
   const gib_dims& d = r.pl.d;
   const Plan& pl = r.pl;
   const Layout& L = r.L;
@@ -692,7 +696,8 @@ static int node_model_backward(const Run& r, const BwdBufs& bb, const float* out
   const Lin& ih = pl.lins[pl.gru_ih];
   const Lin& hh = pl.lins[pl.gru_hh];
   float* sc = r.scratch;
-  GIB_TRY(readout_backward(r, bb, out, dout));
+  if (part != 2) GIB_TRY(readout_backward(r, bb, out, dout));
+  if (part == 1) return 0;
   float* dh = sc + bb.dh;        // d h[t+1]
   float* dh_dir = sc + bb.dh2;   // direct path through the GRU
   for (int t = d.T - 1; t >= 0; --t) {
@@ -806,7 +811,7 @@ static int emn_forward(const Run& r, float* out) {
   return readout_forward(r, out);
 }
 
-static int emn_backward(const Run& r, const BwdBufs& bb, const float* out, const float* dout) {
+static int emn_backward(const Run& r, const BwdBufs& bb, const float* out, const float* dout, int part) {
   const gib_dims& d = r.pl.d;
   const Plan& pl = r.pl;
   const Layout& L = r.L;
@@ -814,8 +819,8 @@ static int emn_backward(const Run& r, const BwdBufs& bb, const float* out, const
   const Lin& ih = pl.lins[pl.gru_ih];
   const Lin& hh = pl.lins[pl.gru_hh];
   float* sc = r.scratch;
-  GIB_TRY(readout_backward(r, bb, out, dout));
-  if (E == 0) return 0;
+  if (part != 2) GIB_TRY(readout_backward(r, bb, out, dout));
+  if (part == 1 || E == 0) return 0;
   const size_t EH = (size_t)E * Hp;
   float* dmem = sc + bb.dmem;      // d mem[t+1]
   float* dmem2 = sc + bb.dmem2;
@@ -973,9 +978,11 @@ void make_bwd(const Run& r, BwdBufs& bb) {
 int model_forward(const Run& r, float* out) {
   return r.pl.d.model == GIB_EMN ? emn_forward(r, out) : node_model_forward(r, out);
 }
-int model_backward(const Run& r, const BwdBufs& bb, const float* out, const float* dout) {
+int model_backward(const Run& r, const BwdBufs& bb, const float* out, const float* dout, int part) {
+  if (part < 0 || part > 2) { set_error("model_backward: part %d", part); return -2; }
   GIB_TRY(dw_begin());
-  const int rc = r.pl.d.model == GIB_EMN ? emn_backward(r, bb, out, dout) : node_model_backward(r, bb, out, dout);
+  const int rc = r.pl.d.model == GIB_EMN ? emn_backward(r, bb, out, dout, part)
+                                         : node_model_backward(r, bb, out, dout, part);
   const int rj = dw_join(r.st);   // the last reduction job runs on the helper side stream: order it before the caller
   return rc ? rc : rj;
 }

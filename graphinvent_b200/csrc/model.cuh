@@ -94,6 +94,6 @@ GraphArrays graph_arrays(void* buf, long long S, int E, int P);
 int make_run(const gib_dims& d, const int* hdr, Run& r);
 void make_bwd(const Run& r, BwdBufs& bb);
 int model_forward(const Run& r, float* out);
-int model_backward(const Run& r, const BwdBufs& bb, const float* out, const float* dout);
+int model_backward(const Run& r, const BwdBufs& bb, const float* out, const float* dout, int part = 0);
 
 }  // namespace gib

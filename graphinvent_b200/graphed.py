@@ -76,7 +76,22 @@ class TrainStep:
             p.grad = v
             o += p.numel()
         self.workspace_bytes = ws_bytes
+        # data parallel: the gradients of the readout parameters (gather.*, APDReadout.*: the tail of the parameter
+        # order, 79 % of the bucket) are final after the first part of the backward; their all-reduce runs on a side
+        # stream while the message-passing backward (second captured graph) still executes
+        self.world = 1
+        if group is not False and torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.world = torch.distributed.get_world_size(group)
+        self.tail_off = total
+        if self.world > 1:
+            names = [n for n, _ in model.named_parameters()]
+            i = len(names)
+            while i > 0 and names[i - 1].startswith(("gather.", "APDReadout.")):
+                i -= 1
+            self.tail_off = sum(p.numel() for p in params[:i])
+            self.comm_stream = torch.cuda.Stream(dev)
         self.graph = None
+        self.graph2 = None
         self.steps = 0
         self._param_ptrs = None
         if warmup:
@@ -100,22 +115,38 @@ class TrainStep:
         check(lib.gib_sum_scaled(F._ptr(self.rows), self.B, 1.0 / self.global_batch, F._ptr(self.loss), st),
               "gib_sum_scaled")
         check(lib.gib_fill_zero(F._ptr(self.gflat), self.gflat.numel() * 4, st), "gib_fill_zero")
-        check(lib.gib_model_backward(bd, self.hdr, F._ptr(self.nodes), F._ptr(self.edges), F._ptr(self.gbuf),
-                                     F._ptr(self.packed), F._ptr(self.ws), F._ptr(self.out), F._ptr(self.dout),
-                                     F._ptr_table(self.views), F._ptr(self.scratch), st), "gib_model_backward")
+        self._backward(1 if self.world > 1 else 0)
+
+    def _backward(self, part):
+        st = F._stream(self.dev)
+        check(lib.gib_model_backward_part(ctypes.byref(self.d), self.hdr, F._ptr(self.nodes), F._ptr(self.edges),
+                                          F._ptr(self.gbuf), F._ptr(self.packed), F._ptr(self.ws), F._ptr(self.out),
+                                          F._ptr(self.dout), F._ptr_table(self.views), F._ptr(self.scratch), part, st),
+              "gib_model_backward_part")
+
+    def _enqueue_all(self):
+        """the whole step's launch sequence, eagerly (warm-up, kernel-class timing)"""
+        self._enqueue()
+        if self.world > 1:
+            self._backward(2)
 
     def capture(self):
         """(re)capture; called by the constructor and again if the parameters were moved (e.g. by FlatAdam)"""
         side = torch.cuda.Stream(self.dev)
         side.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(side):            # warm-up outside capture: lazy per-device init, function attributes
-            self._enqueue()
+            self._enqueue_all()
         torch.cuda.current_stream(self.dev).wait_stream(side)
         torch.cuda.synchronize(self.dev)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             self._enqueue()
         self.graph = g
+        if self.world > 1:
+            g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g2):
+                self._backward(2)
+            self.graph2 = g2
         self._param_ptrs = [p.data_ptr() for p in self.params]
 
     # ---- one step -----------------------------------------------------------------------------------------
@@ -136,10 +167,18 @@ class TrainStep:
             if p.grad is not v:
                 p.grad = v                        # zero_grad(set_to_none=True) of the reference loop (Workflow.py:787)
         self.graph.replay()
-        if self.group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
-                                      and torch.distributed.get_world_size(self.group) > 1):
+        if self.world > 1:
             # per-rank gradients are already scaled by 1/global_batch: a plain sum is the global batch mean
-            torch.distributed.all_reduce(self.gflat, op=torch.distributed.ReduceOp.SUM, group=self.group)
+            dist, cur = torch.distributed, torch.cuda.current_stream(self.dev)
+            grp = self.group if self.group not in (None, False) else None
+            self.comm_stream.wait_stream(cur)
+            with torch.cuda.stream(self.comm_stream):          # readout gradients: overlapped with graph 2
+                if self.tail_off < self.gflat.numel():
+                    dist.all_reduce(self.gflat[self.tail_off:], op=dist.ReduceOp.SUM, group=grp)
+            self.graph2.replay()                               # message-passing backward
+            if self.tail_off > 0:
+                dist.all_reduce(self.gflat[:self.tail_off], op=dist.ReduceOp.SUM, group=grp)
+            cur.wait_stream(self.comm_stream)
         self.optimizer.step()
         F.invalidate_packed_weights()
         self.steps += 1

@@ -123,6 +123,12 @@ int gib_model_forward(const gib_dims* d, const int* hdr_host, const void* nodes,
                       const void* graph_buf, const void* packed, void* workspace, float* out,
                       gib_stream stream);
 size_t gib_model_bwd_scratch_bytes(const gib_dims* d, const int* hdr_host);
+/* The backward in two parts on the same scratch: part 1 = readout only -- afterwards the gradients of the gather.* and
+ * APDReadout.* parameters (the tail of the parameter order, 79 % of the bytes) are final and a data-parallel caller
+ * can start their all-reduce; part 2 = the message passes; part 0 = both (== gib_model_backward). */
+int gib_model_backward_part(const gib_dims* d, const int* hdr_host, const void* nodes, const void* edges,
+                            const void* graph_buf, const void* packed, const void* workspace, const float* out,
+                            const float* dout, float* const* grads, void* scratch, int part, gib_stream stream);
 /* grads[i] (same order / shapes as params) are ACCUMULATED into (+=). */
 int gib_model_backward(const gib_dims* d, const int* hdr_host, const void* nodes, const void* edges,
                        const void* graph_buf, const void* packed, const void* workspace,

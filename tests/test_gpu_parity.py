@@ -450,3 +450,20 @@ def test_fp64_anchored_pretrained_on_all_real_gdb13_rows():
     fx = load_gdb13()
     sd = torch.load(path, map_location="cpu", weights_only=False)
     _fp64_anchored(O.make_constants("GGNN"), sd, fx["nodes"], fx["edges"], fx["apds"], "pretrained x 256 real gdb13 rows")
+
+
+def test_multi_type_bonds_follow_the_reference():
+    """GGNN sums the per-type messages of a multi-type bond like the reference; AttentionGGNN raises, as the
+    reference's AggregationMPNN does on such input (tests/test_oracle.py pins that against the live reference)"""
+    from oracle import mpnn_oracle as O
+    from tests.test_oracle import _multitype_batch
+    C = O.make_constants("GGNN")
+    sd = O.init_state_dict(C, seed=2)
+    nodes, edges = _multitype_batch(C)
+    ref = O.forward(sd, C, nodes, edges)
+    with torch.no_grad():
+        out = _build(C, sd)(nodes.cuda(), edges.cuda()).cpu()
+    assert (out - ref).abs().max().item() <= LOGIT_TOL
+    Ca = O.make_constants("AttGGNN")
+    with pytest.raises(RuntimeError, match="one bond type per bond"):
+        _build(Ca, O.init_state_dict(Ca, seed=2))(nodes.cuda(), edges.cuda())

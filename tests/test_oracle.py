@@ -98,3 +98,33 @@ def test_oracle_training_curve_follows_the_reference(model):
         losses.append(loss.item())
     dev = np.abs(np.array(losses) - z[f"loss/{model}"])
     assert dev[0] <= 1e-6 and dev.max() <= 1e-4, (model, float(dev.max()))
+
+
+def _multitype_batch(C):
+    """two 3-atom molecules; the second carries a bond with two non-zero types (slot 0 of a generation batch
+    accumulates such bonds, GraphGenerator.py:418-423)"""
+    B, N, F, Ef = 2, C.max_n_nodes, C.n_node_features, C.n_edge_features
+    nodes = torch.zeros(B, N, F)
+    edges = torch.zeros(B, N, N, Ef)
+    nodes[:, :3, 0] = 1
+    edges[0, 0, 1, 0] = edges[0, 1, 0, 0] = 1
+    edges[0, 1, 2, 1] = edges[0, 2, 1, 1] = 1
+    edges[1, 0, 1, 0] = edges[1, 1, 0, 0] = 1
+    edges[1, 0, 1, 2] = edges[1, 1, 0, 2] = 1
+    return nodes, edges
+
+
+def test_reference_aggregation_mpnn_rejects_multi_type_bonds():
+    """error behaviour the drop-in mirrors: the reference's AggregationMPNN prologue sizes the neighbour slots by the
+    summed bond VALUES (aggregation_mpnn.py:115-141), so a bond with two non-zero types makes its index assignment
+    raise -- AttentionGGNN does not accept such input in the reference either"""
+    from tests import refimpl
+    if not refimpl.available():
+        pytest.skip("/root/reference not mounted")
+    C = O.make_constants("AttGGNN")
+    net = refimpl.build(C)
+    nodes, edges = _multitype_batch(C)
+    with pytest.raises(RuntimeError):
+        net(nodes, edges)
+    ggnn = refimpl.build(O.make_constants("GGNN"))          # the summation family handles it (sum over the types)
+    assert torch.isfinite(ggnn(nodes, edges)).all()
