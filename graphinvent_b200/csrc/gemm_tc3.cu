@@ -82,7 +82,12 @@ struct Params {
   float* bias_part[MAXP];   // TN: [splits][Nn] partial column sums of G (nullptr: not wanted)
   int nprob;
   int chunk_rows;           // TN: reduction rows per work item (multiple of 32)
+  int diag;                 // timing experiments (gib_tc_debug >> 8; results are wrong with most of them):
+                            //   1 no global stores   2 no epilogue after the drain   4 no split / STTM   8 no W_lo tile + MMAs
+                            //   16 no MMAs   32 no TMA loads   64 no accumulator drain   128 rotate the k-block order per CTA
 };
+enum { DG_NO_STORE = 1, DG_NO_EPI = 2, DG_NO_SPLIT = 4, DG_NO_BLO = 8, DG_NO_MMA = 16, DG_NO_TMA = 32, DG_NO_DRAIN = 64,
+       DG_ROTATE = 128 };
 
 struct Sched {              // computed once per CTA from host values or the device-side row counts
   int M[MAXP], base[MAXP], begin[MAXP + 1], splits[MAXP];
@@ -219,14 +224,19 @@ tc3_gemm_kernel(const __grid_constant__ Maps maps, const Params P) {
         const CUtensorMap* map_a = &maps.a[w.p];
         const CUtensorMap* map_b = &maps.b[w.p];
         const int base = S.base[w.p];
-        for (int kb = 0; kb < w.nkb; ++kb) {
+        const int rot = (P.diag & DG_ROTATE) ? (int)(blockIdx.x % (unsigned)w.nkb) : 0;
+        for (int kb0 = 0; kb0 < w.nkb; ++kb0) {
+          const int kb = (kb0 + rot) % w.nkb;
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* st = smem + stage * STAGE_BYTES;
-          if constexpr (!TN) {
-            mbar_arrive_expect_tx(&full[stage], 3 * TILE_BYTES);
+          if (P.diag & DG_NO_TMA) {
+            mbar_arrive(&full[stage]);
+          } else if constexpr (!TN) {
+            const bool blo = !(P.diag & DG_NO_BLO);
+            mbar_arrive_expect_tx(&full[stage], (blo ? 3 : 2) * TILE_BYTES);
             tma_load_2d(map_a, &full[stage], st, kb * BKF, base + w.m0);
             tma_load_2d(map_b, &full[stage], st + TILE_BYTES, kb * BKF, w.n0);
-            tma_load_2d(&maps.b_lo[w.p], &full[stage], st + 2 * TILE_BYTES, kb * BKF, w.n0);
+            if (blo) tma_load_2d(&maps.b_lo[w.p], &full[stage], st + 2 * TILE_BYTES, kb * BKF, w.n0);
           } else {
             mbar_arrive_expect_tx(&full[stage], 2 * TILE_BYTES);
             const int row = base + w.r0 + kb * BKF;   // 32 reduction rows per stage
@@ -270,13 +280,15 @@ tc3_gemm_kernel(const __grid_constant__ Maps maps, const Params P) {
             idesc = IDESC_TN;
           }
           // grouped by accumulator so that consecutive MMAs chain on the same TMEM tile
+          if (!(P.diag & DG_NO_MMA)) {
 #pragma unroll
-          for (int k = 0; k < BKF / 8; ++k)
-            umma_tf32_ts(tmem_d, a_hi + 8 * k, d_bhi + k * kstep, idesc, (kb | k) != 0);
+            for (int k = 0; k < BKF / 8; ++k)
+              umma_tf32_ts(tmem_d, a_hi + 8 * k, d_bhi + k * kstep, idesc, (kb | k) != 0);
 #pragma unroll
-          for (int k = 0; k < BKF / 8; ++k) {
-            umma_tf32_ts(tmem_x, a_lo + 8 * k, d_bhi + k * kstep, idesc, (kb | k) != 0);
-            umma_tf32_ts(tmem_x, a_hi + 8 * k, d_blo + k * kstep, idesc, 1);
+            for (int k = 0; k < BKF / 8; ++k) {
+              umma_tf32_ts(tmem_x, a_lo + 8 * k, d_bhi + k * kstep, idesc, (kb | k) != 0);
+              if (!(P.diag & DG_NO_BLO)) umma_tf32_ts(tmem_x, a_hi + 8 * k, d_blo + k * kstep, idesc, 1);
+            }
           }
           umma_commit(&empty[stage]);                  // frees the smem stage + its TMEM columns when the MMAs retire
           if (kb == nkb - 1) umma_commit(acc_full);    // accumulators complete
@@ -298,6 +310,11 @@ tc3_gemm_kernel(const __grid_constant__ Maps maps, const Params P) {
       for (int kb = 0; kb < w.nkb; ++kb) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
+        if (P.diag & DG_NO_SPLIT) {
+          mbar_arrive(&a_full[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          continue;
+        }
         const uint32_t sb = smem_u32(smem + stage * STAGE_BYTES);
         uint32_t hi[32], lo[32];
         if constexpr (!TN) {
@@ -376,17 +393,23 @@ tc3_gemm_kernel(const __grid_constant__ Maps maps, const Params P) {
       mbar_wait(acc_full, (uint32_t)(it & 1));
       tc_fence_after();
       float acc[64];
+      if (P.diag & DG_NO_DRAIN) {
 #pragma unroll
-      for (int chunk = 0; chunk < 4; ++chunk) {
-        uint32_t r1[16], r2[16];
-        tmem_ld16(tq + ACC_MAIN + half * 64 + chunk * 16, r1);
-        tmem_ld16(tq + ACC_X + half * 64 + chunk * 16, r2);
-        tmem_ld_wait();
+        for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+      } else {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) acc[chunk * 16 + i] = __uint_as_float(r1[i]) + __uint_as_float(r2[i]);
+        for (int chunk = 0; chunk < 4; ++chunk) {
+          uint32_t r1[16], r2[16];
+          tmem_ld16(tq + ACC_MAIN + half * 64 + chunk * 16, r1);
+          tmem_ld16(tq + ACC_X + half * 64 + chunk * 16, r2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) acc[chunk * 16 + i] = __uint_as_float(r1[i]) + __uint_as_float(r2[i]);
+        }
       }
       tc_fence_before();
       mbar_arrive(acc_empty);                  // the MMA warp may overwrite the accumulators now
+      if (P.diag & DG_NO_EPI) continue;
 #pragma unroll
       for (int chunk = 0; chunk < 4; ++chunk) {
         const int col0 = half * 64 + chunk * 16;
@@ -434,6 +457,7 @@ tc3_gemm_kernel(const __grid_constant__ Maps maps, const Params P) {
               if (n + j >= g.n_valid) v[j] = 0.f;
             }
             float* dst = Cbase + (size_t)m * g.ldc + n;
+            if (P.diag & DG_NO_STORE) continue;
             if (vec_c && n + 3 < g.n_store) {
               *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
             } else {
@@ -646,6 +670,7 @@ int gemm_nt_tc3_group(const GemmNT* ps, int n, cudaStream_t st) {
   }
   if (np == 0) return 0;
   P.nprob = np;
+  P.diag = g_tc_debug >> 8;
   const int grid = (int)(tiles < num_sms ? tiles : num_sms);
   ProfScope prof(PROF_GEMM_NT, work, st);
   tc3_gemm_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps, P);
@@ -720,6 +745,7 @@ int gemm_dw_tc3_partials(const GemmDW* qs, int n, const Dw3Layout& L, float* scr
   }
   P.nprob = n;
   P.chunk_rows = L.chunk_rows;
+  P.diag = g_tc_debug >> 8;
   const int grid = (int)(items < num_sms ? items : num_sms);
   tc3_gemm_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps, P);
   GIB_LAUNCH_CHECK();

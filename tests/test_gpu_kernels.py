@@ -176,7 +176,7 @@ def test_tcgen05_linear_planes_both_generations(gen, M, N, K, act):
     W = torch.randn(N, K, device="cuda") / K ** 0.5
     b = torch.randn(N, device="cuda")
     hi, lo = _planes(lib, check, W)
-    assert torch.equal((hi.double() + lo.double()).float(), W) or (hi.double() + lo.double() - W.double()).abs().max() < 1e-9
+    assert (hi.double() + lo.double() - W.double()).abs().max().item() <= 2.0 ** -21 * W.abs().max().item()   # two 11-bit pieces
     Y = torch.full((M, N), float("nan"), device="cuda")
     lib.gib_tc_debug(1 if gen == 1 else 0)
     try:
