@@ -85,9 +85,10 @@ struct Params {
   int diag;                 // timing experiments (gib_tc_debug >> 8; results are wrong with most of them):
                             //   1 no global stores   2 no epilogue after the drain   4 no split / STTM   8 no W_lo tile + MMAs
                             //   16 no MMAs   32 no TMA loads   64 no accumulator drain   128 rotate the k-block order per CTA
+                            //   256 interleave the MMAs of the two accumulators
 };
 enum { DG_NO_STORE = 1, DG_NO_EPI = 2, DG_NO_SPLIT = 4, DG_NO_BLO = 8, DG_NO_MMA = 16, DG_NO_TMA = 32, DG_NO_DRAIN = 64,
-       DG_ROTATE = 128 };
+       DG_ROTATE = 128, DG_INTERLEAVE = 256 };
 
 struct Sched {              // computed once per CTA from host values or the device-side row counts
   int M[MAXP], base[MAXP], begin[MAXP + 1], splits[MAXP];
@@ -156,7 +157,19 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
   lo = to_tf32(x - __uint_as_float(hi));
 }
 
-template <bool TN>
+// EPI: epilogue specialisation shared by every problem of the launch.  The per-element epilogue must stay a few
+// instructions: a generic one (run-time mode / activation / alignment branches for each of the 64 outputs of a thread)
+// compiled to ~80 KB of straight-line code, missed the instruction cache on every tile and made the 8 epilogue warps
+// the bottleneck of the whole kernel (measured: 236 us with it, 108 us without, profiles/r02_tc3_probe.md).
+//   EPI_SPEC_GENERIC   any mode / activation / alignment, chunk by chunk straight from TMEM (accumulators are held
+//                      until the tile is stored: rare shapes only -- unaligned or narrow outputs)
+//   EPI_SPEC_SELU      C = selu(acc + bias)          EPI_SPEC_LINEAR  C = acc (+ bias)
+//   EPI_SPEC_DSELU     C = acc * selu'(aux)          EPI_SPEC_ADD     C = acc + aux
+// The specialised ones need 16-byte aligned rows (ldc, ldaux multiples of 4 floats) and n_store == n_valid, a
+// multiple of 4 -- the padded-layout contract of every internal buffer.
+enum { EPI_SPEC_GENERIC = 0, EPI_SPEC_SELU = 1, EPI_SPEC_LINEAR = 2, EPI_SPEC_DSELU = 3, EPI_SPEC_ADD = 4 };
+
+template <bool TN, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc3_gemm_kernel(const __grid_constant__ Maps maps, const Params P) {
   extern __shared__ uint8_t smem_raw[];
@@ -175,7 +188,7 @@ tc3_gemm_kernel(const __grid_constant__ Maps maps, const Params P) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&a_full[s], 32 * SPL_WARPS);
+      mbar_init(&a_full[s], TN ? 32 * (SPL_WARPS + EPI_WARPS) : 32 * SPL_WARPS);
       mbar_init(&empty[s], 1);
     }
     mbar_init(acc_full, 1);
@@ -280,7 +293,14 @@ tc3_gemm_kernel(const __grid_constant__ Maps maps, const Params P) {
             idesc = IDESC_TN;
           }
           // grouped by accumulator so that consecutive MMAs chain on the same TMEM tile
-          if (!(P.diag & DG_NO_MMA)) {
+          if (P.diag & DG_INTERLEAVE) {          // experiment: alternate the two accumulators k-step by k-step
+#pragma unroll
+            for (int k = 0; k < BKF / 8; ++k) {
+              umma_tf32_ts(tmem_d, a_hi + 8 * k, d_bhi + k * kstep, idesc, (kb | k) != 0);
+              umma_tf32_ts(tmem_x, a_lo + 8 * k, d_bhi + k * kstep, idesc, (kb | k) != 0);
+              umma_tf32_ts(tmem_x, a_hi + 8 * k, d_blo + k * kstep, idesc, 1);
+            }
+          } else if (!(P.diag & DG_NO_MMA)) {
 #pragma unroll
             for (int k = 0; k < BKF / 8; ++k)
               umma_tf32_ts(tmem_d, a_hi + 8 * k, d_bhi + k * kstep, idesc, (kb | k) != 0);
@@ -342,26 +362,6 @@ tc3_gemm_kernel(const __grid_constant__ Maps maps, const Params P) {
         }
         tmem_st32(trow + stage * A_STAGE_COLS, hi);
         tmem_st32(trow + stage * A_STAGE_COLS + 32, lo);
-        if constexpr (TN) {
-          // X tile (MN-major B operand): raw -> hi in place, lo into the sibling tile at the same (swizzled) offset
-          const int valid = w.rows - kb * BKF;
-          const uint32_t xb = sb + TILE_BYTES;
-#pragma unroll
-          for (int i = 0; i < TILE_BYTES / 16 / 128; ++i) {
-            const uint32_t c = (uint32_t)(t + i * 128);       // 16-byte chunk index; 8 chunks per 128 B row
-            const int m = (int)((c & 255u) >> 3);             // reduction row inside its 4 KB box
-            float4 v = lds128(xb + c * 16);
-            if (m >= valid) v = make_float4(0.f, 0.f, 0.f, 0.f);
-            uint32_t h[4], l[4];
-            split_tf32(v.x, h[0], l[0]); split_tf32(v.y, h[1], l[1]);
-            split_tf32(v.z, h[2], l[2]); split_tf32(v.w, h[3], l[3]);
-            sts128(xb + c * 16, make_float4(__uint_as_float(h[0]), __uint_as_float(h[1]), __uint_as_float(h[2]),
-                                            __uint_as_float(h[3])));
-            sts128(xb + TILE_BYTES + c * 16, make_float4(__uint_as_float(l[0]), __uint_as_float(l[1]),
-                                                         __uint_as_float(l[2]), __uint_as_float(l[3])));
-          }
-          fence_proxy_async();         // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-        }
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&a_full[stage]);
@@ -380,93 +380,180 @@ tc3_gemm_kernel(const __grid_constant__ Maps maps, const Params P) {
     const uint32_t stg = smem_u32(smem + OFF_STG + ew * EPI_STG_BYTES);
     const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
     const int rr = lane >> 2, c4 = lane & 3;
+    const uint32_t st_wr = stg + lane * 64;                          // this lane's staging row (written)
+    const uint32_t swz_wr = ((uint32_t)lane >> 1) & 3u;
     int it = 0;
+    int stage = 0;
+    uint32_t phase = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
       const Item w = decode_item<TN>(P, S, item);
+      if constexpr (TN) {
+        // the epilogue warps idle during a work item's k-loop: they split the X tile (MN-major B operand) of every
+        // k-block -- raw -> hi in place, lo into the sibling tile at the same (swizzled) offset
+        const int et = threadIdx.x - 32 * (2 + SPL_WARPS);           // 0..255
+        for (int kb = 0; kb < w.nkb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          if (!(P.diag & DG_NO_SPLIT)) {
+            const int valid = w.rows - kb * BKF;
+            const uint32_t xb = smem_u32(smem + stage * STAGE_BYTES) + TILE_BYTES;
+#pragma unroll
+            for (int i = 0; i < TILE_BYTES / 16 / (32 * EPI_WARPS); ++i) {
+              const uint32_t c = (uint32_t)(et + i * 32 * EPI_WARPS);   // 16-byte chunk index; 8 chunks per 128 B row
+              const int m = (int)((c & 255u) >> 3);                     // reduction row inside its 4 KB box
+              float4 v = lds128(xb + c * 16);
+              if (m >= valid) v = make_float4(0.f, 0.f, 0.f, 0.f);      // rows past the chunk / the row count
+              uint32_t h[4], l[4];
+              split_tf32(v.x, h[0], l[0]); split_tf32(v.y, h[1], l[1]);
+              split_tf32(v.z, h[2], l[2]); split_tf32(v.w, h[3], l[3]);
+              sts128(xb + c * 16, make_float4(__uint_as_float(h[0]), __uint_as_float(h[1]), __uint_as_float(h[2]),
+                                              __uint_as_float(h[3])));
+              sts128(xb + TILE_BYTES + c * 16, make_float4(__uint_as_float(l[0]), __uint_as_float(l[1]),
+                                                           __uint_as_float(l[2]), __uint_as_float(l[3])));
+            }
+            fence_proxy_async();       // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+          }
+          mbar_arrive(&a_full[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
       const GemmNT& g = P.g[w.p];
       const int Mrows = TN ? P.tn_nn[w.p] : S.M[w.p];
       const size_t row_base = TN ? (size_t)0 : (size_t)S.base[w.p];
       float* const Cbase = g.C + (TN ? (size_t)w.z * P.tn_nn[w.p] * g.ldc : row_base * g.ldc);
       const float* const Xbase = g.aux ? g.aux + row_base * g.ldaux : nullptr;
-      const bool vec_c = (g.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
-      const bool vec_x = g.aux && (g.ldaux & 3) == 0 && ((reinterpret_cast<uintptr_t>(g.aux) & 15) == 0);
+      const int ldc = g.ldc, ldaux = g.ldaux, n_store = g.n_store;
+      const int mrow0 = w.m0 + q * 32 + rr;                          // first of this lane's 4 output rows (stride 8)
+      const int ncol0 = w.n0 + half * 64 + c4 * 4;                   // first of this lane's 4 column groups (stride 16)
       mbar_wait(acc_full, (uint32_t)(it & 1));
       tc_fence_after();
-      float acc[64];
-      if (P.diag & DG_NO_DRAIN) {
+      if constexpr (EPI != EPI_SPEC_GENERIC) {
+        float acc[64];
+        if (P.diag & DG_NO_DRAIN) {
 #pragma unroll
-        for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+          for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+        } else {
+#pragma unroll
+          for (int chunk = 0; chunk < 4; ++chunk) {
+            uint32_t r1[16], r2[16];
+            tmem_ld16(tq + ACC_MAIN + half * 64 + chunk * 16, r1);
+            tmem_ld16(tq + ACC_X + half * 64 + chunk * 16, r2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[chunk * 16 + i] = __uint_as_float(r1[i]) + __uint_as_float(r2[i]);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(acc_empty);                  // the MMA warp may overwrite the accumulators now
+        if (P.diag & DG_NO_EPI) continue;
+        const float* const bias = g.bias;
+#pragma unroll
+        for (int chunk = 0; chunk < 4; ++chunk) {
+          __syncwarp();
+          // lane = tile row; 16-byte chunk j of row `lane` is stored at chunk (j ^ ((lane >> 1) & 3)): 8 consecutive
+          // rows hit 8 distinct bank groups on the write, and the 2 rows x 4 chunks of a read phase do as well
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4)
+            sts128(st_wr + (((uint32_t)j4 ^ swz_wr) << 4),
+                   make_float4(acc[chunk * 16 + j4 * 4 + 0], acc[chunk * 16 + j4 * 4 + 1],
+                               acc[chunk * 16 + j4 * 4 + 2], acc[chunk * 16 + j4 * 4 + 3]));
+          __syncwarp();
+          const int n = ncol0 + chunk * 16;
+          if (n < n_store) {
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if constexpr (EPI == EPI_SPEC_SELU || EPI == EPI_SPEC_LINEAR)
+              if (bias) b4 = __ldg(reinterpret_cast<const float4*>(bias + n));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int row = i * 8 + rr;
+              const int m = mrow0 + i * 8;
+              if (m < Mrows) {
+                float4 v = lds128(stg + row * 64 + (((uint32_t)c4 ^ (((uint32_t)row >> 1) & 3u)) << 4));
+                if constexpr (EPI == EPI_SPEC_SELU) {
+                  v.x = act_fast(v.x + b4.x, ACT_SELU); v.y = act_fast(v.y + b4.y, ACT_SELU);
+                  v.z = act_fast(v.z + b4.z, ACT_SELU); v.w = act_fast(v.w + b4.w, ACT_SELU);
+                } else if constexpr (EPI == EPI_SPEC_LINEAR) {
+                  v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+                } else {
+                  const float4 x = __ldg(reinterpret_cast<const float4*>(Xbase + (size_t)m * ldaux + n));
+                  if constexpr (EPI == EPI_SPEC_DSELU) {
+                    v.x *= dselu_from_out(x.x); v.y *= dselu_from_out(x.y);
+                    v.z *= dselu_from_out(x.z); v.w *= dselu_from_out(x.w);
+                  } else {
+                    v.x += x.x; v.y += x.y; v.z += x.z; v.w += x.w;
+                  }
+                }
+                if (!(P.diag & DG_NO_STORE)) *reinterpret_cast<float4*>(Cbase + (size_t)m * ldc + n) = v;
+              }
+            }
+          }
+        }
       } else {
-#pragma unroll
+        // generic: one 16-column chunk at a time straight from TMEM (no 64-register drain, compact code)
+        const bool vec_c = (ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
+        const bool vec_x = g.aux && (ldaux & 3) == 0 && ((reinterpret_cast<uintptr_t>(g.aux) & 15) == 0);
+        const int mode = g.mode, act = g.act, n_valid = g.n_valid, Ncols = g.N;
+#pragma unroll 1
         for (int chunk = 0; chunk < 4; ++chunk) {
           uint32_t r1[16], r2[16];
           tmem_ld16(tq + ACC_MAIN + half * 64 + chunk * 16, r1);
           tmem_ld16(tq + ACC_X + half * 64 + chunk * 16, r2);
           tmem_ld_wait();
+          __syncwarp();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) acc[chunk * 16 + i] = __uint_as_float(r1[i]) + __uint_as_float(r2[i]);
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(acc_empty);                  // the MMA warp may overwrite the accumulators now
-      if (P.diag & DG_NO_EPI) continue;
+          for (int j4 = 0; j4 < 4; ++j4)
+            sts128(st_wr + (((uint32_t)j4 ^ swz_wr) << 4),
+                   make_float4(__uint_as_float(r1[j4 * 4 + 0]) + __uint_as_float(r2[j4 * 4 + 0]),
+                               __uint_as_float(r1[j4 * 4 + 1]) + __uint_as_float(r2[j4 * 4 + 1]),
+                               __uint_as_float(r1[j4 * 4 + 2]) + __uint_as_float(r2[j4 * 4 + 2]),
+                               __uint_as_float(r1[j4 * 4 + 3]) + __uint_as_float(r2[j4 * 4 + 3])));
+          __syncwarp();
+          const int n = ncol0 + chunk * 16;
+          if (n < n_store && !(P.diag & DG_NO_EPI)) {
+            float bj[4] = {0.f, 0.f, 0.f, 0.f};
+            if (mode == EPI_ACT && g.bias) {
 #pragma unroll
-      for (int chunk = 0; chunk < 4; ++chunk) {
-        const int col0 = half * 64 + chunk * 16;
-        __syncwarp();
-        // lane = tile row; 16-byte chunk j of row `lane` is stored at chunk (j ^ ((lane >> 1) & 3)): 8 consecutive
-        // rows hit 8 distinct bank groups on the write, and the 2 rows x 4 chunks of a read phase do as well
+              for (int j = 0; j < 4; ++j)
+                if (n + j < Ncols) bj[j] = __ldg(g.bias + n + j);
+            }
+#pragma unroll 1
+            for (int i = 0; i < 4; ++i) {
+              const int row = i * 8 + rr;
+              const int m = mrow0 + i * 8;
+              if (m >= Mrows) continue;
+              const float4 a4 = lds128(stg + row * 64 + (((uint32_t)c4 ^ (((uint32_t)row >> 1) & 3u)) << 4));
+              float v[4] = {a4.x, a4.y, a4.z, a4.w};
+              float x[4] = {0.f, 0.f, 0.f, 0.f};
+              if (mode != EPI_ACT) {
+                const float* ax = Xbase + (size_t)m * ldaux + n;
+                if (vec_x && n + 3 < n_store) {
+                  const float4 t4 = *reinterpret_cast<const float4*>(ax);
+                  x[0] = t4.x; x[1] = t4.y; x[2] = t4.z; x[3] = t4.w;
+                } else {
 #pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4)
-          sts128(stg + lane * 64 + (((uint32_t)j4 ^ (((uint32_t)lane >> 1) & 3u)) << 4),
-                 make_float4(acc[chunk * 16 + j4 * 4 + 0], acc[chunk * 16 + j4 * 4 + 1], acc[chunk * 16 + j4 * 4 + 2],
-                             acc[chunk * 16 + j4 * 4 + 3]));
-        __syncwarp();
-        const int n = w.n0 + col0 + c4 * 4;
-        if (n < g.n_store) {
-          float bj[4] = {0.f, 0.f, 0.f, 0.f};
-          if (g.mode == EPI_ACT && g.bias) {
+                  for (int j = 0; j < 4; ++j)
+                    if (n + j < n_store) x[j] = ax[j];
+                }
+              }
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (n + j < g.N) bj[j] = __ldg(g.bias + n + j);
-          }
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int row = i * 8 + rr;
-            const int m = w.m0 + q * 32 + row;
-            if (m >= Mrows) continue;
-            const float4 a4 = lds128(stg + row * 64 + (((uint32_t)c4 ^ (((uint32_t)row >> 1) & 3u)) << 4));
-            float v[4] = {a4.x, a4.y, a4.z, a4.w};
-            float x[4] = {0.f, 0.f, 0.f, 0.f};
-            if (g.mode != EPI_ACT) {
-              const float* ax = Xbase + (size_t)m * g.ldaux + n;
-              if (vec_x && n + 3 < g.n_store) {
-                const float4 t4 = *reinterpret_cast<const float4*>(ax);
-                x[0] = t4.x; x[1] = t4.y; x[2] = t4.z; x[3] = t4.w;
+              for (int j = 0; j < 4; ++j) {
+                if (mode == EPI_ACT) v[j] = act_fast(v[j] + bj[j], act);
+                else if (mode == EPI_MUL_DACT) v[j] = v[j] * dact_from_out(x[j], act);
+                else v[j] = v[j] + x[j];
+                if (n + j >= n_valid) v[j] = 0.f;
+              }
+              float* dst = Cbase + (size_t)m * ldc + n;
+              if (vec_c && n + 3 < n_store) {
+                *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
               } else {
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                  if (n + j < g.n_store) x[j] = ax[j];
+                  if (n + j < n_store) dst[j] = v[j];
               }
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (g.mode == EPI_ACT) v[j] = act_fast(v[j] + bj[j], g.act);
-              else if (g.mode == EPI_MUL_DACT) v[j] = v[j] * dact_from_out(x[j], g.act);
-              else v[j] = v[j] + x[j];
-              if (n + j >= g.n_valid) v[j] = 0.f;
-            }
-            float* dst = Cbase + (size_t)m * g.ldc + n;
-            if (P.diag & DG_NO_STORE) continue;
-            if (vec_c && n + 3 < g.n_store) {
-              *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                if (n + j < g.n_store) dst[j] = v[j];
             }
           }
         }
+        tc_fence_before();
+        mbar_arrive(acc_empty);
       }
     }
   }
@@ -620,12 +707,31 @@ static int prepare(int* num_sms_out) {
   DevInfo& d = g_dev[dev];
   if (!d.attr_done) {   // function attributes are per device
     GIB_CUDA_TRY(cudaDeviceGetAttribute(&d.num_sms, cudaDevAttrMultiProcessorCount, dev));
-    GIB_CUDA_TRY(cudaFuncSetAttribute(tc3_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    GIB_CUDA_TRY(cudaFuncSetAttribute(tc3_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    GIB_CUDA_TRY(cudaFuncSetAttribute(tc3_gemm_kernel<false, EPI_SPEC_GENERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    GIB_CUDA_TRY(cudaFuncSetAttribute(tc3_gemm_kernel<false, EPI_SPEC_SELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    GIB_CUDA_TRY(cudaFuncSetAttribute(tc3_gemm_kernel<false, EPI_SPEC_LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    GIB_CUDA_TRY(cudaFuncSetAttribute(tc3_gemm_kernel<false, EPI_SPEC_DSELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    GIB_CUDA_TRY(cudaFuncSetAttribute(tc3_gemm_kernel<false, EPI_SPEC_ADD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    GIB_CUDA_TRY(cudaFuncSetAttribute(tc3_gemm_kernel<true, EPI_SPEC_LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     d.attr_done = true;
   }
   *num_sms_out = d.num_sms;
   return 0;
+}
+
+// which compact epilogue a problem can use (EPI_SPEC_GENERIC: none)
+static int epi_spec(const GemmNT& p) {
+  auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  if ((p.ldc & 3) || !al(p.C) || (p.n_store & 3) || p.n_valid != p.n_store) return EPI_SPEC_GENERIC;
+  if (p.mode == EPI_ACT) {
+    if (p.bias && (!al(p.bias) || p.N < p.n_store)) return EPI_SPEC_GENERIC;
+    if (p.act == ACT_SELU) return EPI_SPEC_SELU;
+    if (p.act == ACT_NONE) return EPI_SPEC_LINEAR;
+    return EPI_SPEC_GENERIC;
+  }
+  if (!p.aux || (p.ldaux & 3) || !al(p.aux)) return EPI_SPEC_GENERIC;
+  if (p.mode == EPI_MUL_DACT) return p.act == ACT_SELU ? EPI_SPEC_DSELU : EPI_SPEC_GENERIC;
+  return EPI_SPEC_ADD;
 }
 
 }  // namespace tc3
@@ -654,10 +760,13 @@ int gemm_nt_tc3_group(const GemmNT* ps, int n, cudaStream_t st) {
   double work = 0;
   long long tiles = 0;
   int np = 0;
+  int spec = -1;
   for (int i = 0; i < n; ++i) {
     const GemmNT& p = ps[i];
     if (p.M <= 0 || p.N <= 0) continue;
     if (!tc3_eligible(p)) { set_error("gemm_nt_tc3: operands violate the TMA alignment / pre-split contract"); return -2; }
+    const int sp = epi_spec(p);
+    spec = (spec < 0 || spec == sp) ? sp : EPI_SPEC_GENERIC;     // one epilogue specialisation per launch
     GIB_TRY(make_map(&maps.a[np], p.A, p.M, p.K, p.lda, BM, CU_TENSOR_MAP_SWIZZLE_128B));
     GIB_TRY(make_map(&maps.b[np], p.B_hi, p.N, p.K, p.ldb, BN, CU_TENSOR_MAP_SWIZZLE_128B));
     GIB_TRY(make_map(&maps.b_lo[np], p.B_lo, p.N, p.K, p.ldb, BN, CU_TENSOR_MAP_SWIZZLE_128B));
@@ -673,7 +782,13 @@ int gemm_nt_tc3_group(const GemmNT* ps, int n, cudaStream_t st) {
   P.diag = g_tc_debug >> 8;
   const int grid = (int)(tiles < num_sms ? tiles : num_sms);
   ProfScope prof(PROF_GEMM_NT, work, st);
-  tc3_gemm_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps, P);
+  switch (spec) {
+    case EPI_SPEC_SELU: tc3_gemm_kernel<false, EPI_SPEC_SELU><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps, P); break;
+    case EPI_SPEC_LINEAR: tc3_gemm_kernel<false, EPI_SPEC_LINEAR><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps, P); break;
+    case EPI_SPEC_DSELU: tc3_gemm_kernel<false, EPI_SPEC_DSELU><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps, P); break;
+    case EPI_SPEC_ADD: tc3_gemm_kernel<false, EPI_SPEC_ADD><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps, P); break;
+    default: tc3_gemm_kernel<false, EPI_SPEC_GENERIC><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps, P); break;
+  }
   GIB_LAUNCH_CHECK();
   return 0;
 }
@@ -747,7 +862,7 @@ int gemm_dw_tc3_partials(const GemmDW* qs, int n, const Dw3Layout& L, float* scr
   P.chunk_rows = L.chunk_rows;
   P.diag = g_tc_debug >> 8;
   const int grid = (int)(items < num_sms ? items : num_sms);
-  tc3_gemm_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps, P);
+  tc3_gemm_kernel<true, EPI_SPEC_LINEAR><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps, P);
   GIB_LAUNCH_CHECK();
   return 0;
 }

@@ -259,7 +259,8 @@ __global__ void __launch_bounds__(256) scatter_sum_kernel(float4* __restrict__ o
     if (s[k] < S) st_row<HINT>(out + s[k] * ld4 + c, acc[k]);
 }
 
-int g_scatter_variant = 3;     // 0: 1 slot / thread, default caching   1: 2 slots   2: 1 slot + streaming hints   3: 2 slots + hints
+// measured at the C4 shape (profiles/r02_k2_variants.md): 0: 61.3 us, 1: 65.9 us, 2: 46.3 us (0.68 of the copy peak), 3: 59.6 us
+int g_scatter_variant = 2;     // 0: 1 slot / thread, default caching   1: 2 slots   2: 1 slot + streaming hints   3: 2 slots + hints
 
 int scatter_sum(float* out, const float* msg, int ld, const int* ptr, const int* ent, const float* w, int accumulate,
                 long long S, cudaStream_t st, double bytes) {

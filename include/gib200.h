@@ -89,7 +89,7 @@ int gib_get_tensor_cores(void);
  * process-wide, A/B measurements only.  Capacity mode needs the default. */
 void gib_tc_debug(int mode);
 /* K2 scatter-aggregate variant (A/B measurements): bit 0 = two slots per thread, bit 1 = streaming cache hints;
- * default 3.  Results are identical across variants. */
+ * default 2 (the fastest at the C4 shape).  Results are identical across variants. */
 void gib_scatter_variant(int v);
 /* streaming multiprocessors of the current device (grid sizing of the persistent kernels) */
 int gib_device_sm_count(void);

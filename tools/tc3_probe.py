@@ -14,8 +14,8 @@ P = lambda t: ctypes.c_void_p(t.data_ptr() if t is not None else 0)
 st = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 VARIANTS = [(0, "product"), (1, "no global stores"), (2, "no epilogue after the drain"), (2 | 64, "no drain, no epilogue"),
             (4, "no split / STTM"), (8, "no W_lo tile and MMAs"), (16, "no MMAs"), (32, "no TMA loads"),
-            (4 | 16 | 2 | 64, "TMA only"), (32 | 4 | 2 | 64, "MMA only"), (128, "k-block order rotated per CTA"),
-            (128 | 2, "rotated, no epilogue")]
+            (4 | 16 | 2 | 64, "TMA only"), (32 | 4 | 2 | 64, "MMA only"), (32 | 4 | 2 | 64 | 256, "MMA only, interleaved"),
+            (256, "MMAs interleaved")]
 shapes = [tuple(int(v) for v in a.split("x")) for a in sys.argv[1:]] or [(155648, 256, 256), (23808, 256, 256),
                                                                          (23808, 256, 128), (13312, 512, 512)]
 
