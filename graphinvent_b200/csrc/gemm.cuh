@@ -59,13 +59,15 @@ struct GemmDW {
   const int* base_dev = nullptr;
 };
 
+constexpr int kTc3MaxProblems = 16;   // problems per launch of the second-generation tcgen05 kernel
+
 // scratch layout of one grouped weight-gradient launch of the second-generation tcgen05 kernel (gemm_tc3.cu)
 struct Dw3Layout {
-  int chunk_rows;            // reduction rows per work item
-  int cap_splits[4];         // split capacity per problem (the live count may be smaller: device-side row counts)
-  size_t part_off[4];        // float offsets of [cap_splits][Nn][Kk] partial products
-  size_t bias_off[4];        // float offsets of [cap_splits][Nn] partial column sums
-  size_t floats;             // total
+  int chunk_rows;                          // reduction rows per work item
+  int cap_splits[kTc3MaxProblems];         // split capacity per problem (the live count may be smaller: device-side row counts)
+  size_t part_off[kTc3MaxProblems];        // float offsets of [cap_splits][Nn][Kk] partial products
+  size_t bias_off[kTc3MaxProblems];        // float offsets of [cap_splits][Nn] partial column sums
+  size_t floats;                           // total
 };
 
 int gemm_nt(const GemmNT& p, cudaStream_t st);      // dispatches to the tcgen05 path when enabled and eligible
@@ -73,10 +75,18 @@ int gemm_nt_simt(const GemmNT& p, cudaStream_t st);
 int gemm_nt_tc(const GemmNT& p, cudaStream_t st);
 int gemm_nt_tc_group(const GemmNT* ps, int n, cudaStream_t st);   // n <= 4 independent problems, one launch
 int gemm_nt_group(const GemmNT* ps, int n, cudaStream_t st);      // dispatcher: grouped tcgen05 launch or per-problem
+bool gemm_nt_chain_ok(const GemmNT* ps, int n);                   // can these run as one dependent-chain launch?
+int gemm_nt_chain(const GemmNT* ps, const int* dep, int n, int* flags, cudaStream_t st);
 bool tc_eligible(const GemmNT& p);
 // second-generation kernel (gemm_tc3.cu): activation operand split in registers and fed through tensor memory
 bool tc3_eligible(const GemmNT& p);
 int gemm_nt_tc3_group(const GemmNT* ps, int n, cudaStream_t st);
+// Dependent chain in ONE persistent launch: problem i consumes (A operand) what problem dep[i] produces (dep[i] < i,
+// -1 = independent) with the same row range; work flows from layer to layer row block by row block through counters in
+// `flags` (device ints, >= tc3_chain_flag_ints(ps, n), zeroed here).  No per-layer launch, prologue, tail or wave
+// quantisation.
+size_t tc3_chain_flag_ints(const GemmNT* ps, int n);
+int gemm_nt_tc3_chain(const GemmNT* ps, const int* dep, int n, int* flags, cudaStream_t st);
 bool tc3_dw_eligible(const GemmDW& q);
 void tc3_dw_layout(const GemmDW* qs, int n, long long plan_rows, Dw3Layout* L);
 int gemm_dw_tc3_partials(const GemmDW* qs, int n, const Dw3Layout& L, float* scratch, cudaStream_t st);

@@ -206,6 +206,25 @@ int gemm_nt_group(const GemmNT* ps, int n, cudaStream_t st) {
   return 0;
 }
 
+// Dependent chain (the layers of sibling MLPs): ONE persistent tensor-core launch when every member qualifies,
+// else layer by layer through gemm_nt_group (members of one layer = consecutive problems with equal `layer`).
+bool gemm_nt_chain_ok(const GemmNT* ps, int n) {
+  if (!g_use_tc || !use_tc3() || n < 2 || n > kTc3MaxProblems) return false;
+  long long tiles = 0;
+  bool dyn = false;
+  for (int i = 0; i < n; ++i) {
+    const GemmNT& p = ps[i];
+    if (p.M <= 0 || p.N <= 0) continue;
+    if (!tc3_eligible(p) || p.N < 48 || p.K < 32) return false;
+    if (p.m_dev) dyn = true;
+    tiles += (long long)ceil_div(p.M, 128) * ceil_div(p.N, 128);
+  }
+  return dyn || tiles >= 16;      // small members ride along; a tiny chain is not worth a 148-CTA launch
+}
+int gemm_nt_chain(const GemmNT* ps, const int* dep, int n, int* flags, cudaStream_t st) {
+  return gemm_nt_tc3_chain(ps, dep, n, flags, st);
+}
+
 int gemm_nt_simt(const GemmNT& p, cudaStream_t st) {
   if (p.M <= 0 || p.N <= 0) return 0;
   if (p.K % BK != 0 || (p.lda & 3) || (p.ldb & 3) || p.K <= 0) {
@@ -549,30 +568,40 @@ void gemm_dw_plan(int M, int Nn, int Kk, int* splits, int* chunk) {
 // one fixed-order reduction launch on the side stream; falls back to member-by-member when the group is not eligible
 int gemm_dw_group(const GemmDW* qs, int n, long long plan_rows, cudaStream_t st) {
   if (n < 1) return 0;
-  if (n > 4) { set_error("gemm_dw_group: %d problems (max 4)", n); return -2; }
-  bool ok = g_use_tc && use_tc3(), dyn = false;
+  if (n > kTc3MaxProblems) { set_error("gemm_dw_group: %d problems (max %d)", n, kTc3MaxProblems); return -2; }
+  const bool tc3 = g_use_tc && use_tc3();
+  bool dyn = false;
   long long rows = 0;
   double work = 0;
-  GemmDW live[4];
-  int nl = 0;
+  GemmDW live[kTc3MaxProblems];      // members that run in the grouped tensor-core launch
+  GemmDW rest[kTc3MaxProblems];      // too small / unaligned for it: one by one
+  int nl = 0, nr = 0;
   for (int i = 0; i < n; ++i) {
-    if (qs[i].m_dev) dyn = true;
-    if (qs[i].M <= 0) continue;
-    if (qs[i].scratch != qs[0].scratch || qs[i].half_floats != qs[0].half_floats) ok = false;
-    if (!tc3_dw_eligible(qs[i]) || qs[i].Nn < 32 || qs[i].Kk < 32) ok = false;
-    rows += qs[i].M;
-    work += qs[i].work > 0 ? qs[i].work : 2.0 * qs[i].M * (double)qs[i].R * qs[i].C;
-    live[nl++] = qs[i];
+    const GemmDW& q = qs[i];
+    if (q.M <= 0) continue;
+    const bool good = tc3 && tc3_dw_eligible(q) && q.Nn >= 32 && q.Kk >= 32 && q.scratch == qs[0].scratch &&
+                      q.half_floats == qs[0].half_floats;
+    if (q.m_dev) {
+      dyn = true;
+      if (!good) {
+        set_error("gemm_dw_group: device-side row counts need the tcgen05 path (tensor cores on, aligned operands)");
+        return -2;
+      }
+    }
+    if (good) {
+      rows += q.M;
+      work += q.work > 0 ? q.work : 2.0 * q.M * (double)q.R * q.C;
+      live[nl++] = q;
+    } else {
+      rest[nr++] = q;
+    }
   }
+  if (nl && !dyn && rows < 2048) {           // not worth a tensor-core launch
+    for (int i = 0; i < nl; ++i) rest[nr++] = live[i];
+    nl = 0;
+  }
+  for (int i = 0; i < nr; ++i) GIB_TRY(gemm_dw(rest[i], st));
   if (nl == 0) return 0;
-  if (dyn && !ok) {
-    set_error("gemm_dw_group: device-side row counts need the tcgen05 path (tensor cores on, aligned operands)");
-    return -2;
-  }
-  if (!ok || (!dyn && rows < 2048)) {
-    for (int i = 0; i < nl; ++i) GIB_TRY(gemm_dw(live[i], st));
-    return 0;
-  }
   ProfScope prof(PROF_GEMM_DW, work, st);
   DwSide* d;
   GIB_TRY(dw_side(&d));
@@ -605,7 +634,8 @@ int gemm_dw(const GemmDW& q, cudaStream_t st) {
     set_error("gemm_dw: ldg=%d ldx=%d Nn=%d Kk=%d violate the padded-layout contract", q.ldg, q.ldx, q.Nn, q.Kk);
     return -2;
   }
-  if (q.m_dev || (g_use_tc && use_tc3() && q.dW && q.M >= 2048 && q.Nn >= 32 && q.Kk >= 32 && tc3_dw_eligible(q)))
+  if (q.m_dev || (g_use_tc && use_tc3() && q.dW && q.M >= 2048 && q.Nn >= 32 && q.Kk >= 32 && tc3_dw_eligible(q) &&
+                  q.half_floats > 0))
     return gemm_dw_group(&q, 1, 0, st);
   ProfScope prof(PROF_GEMM_DW, q.work > 0 ? q.work : 2.0 * q.M * (double)q.R * q.C, st);
   DwSide* d;

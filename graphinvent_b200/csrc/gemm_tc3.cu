@@ -54,12 +54,12 @@ constexpr int NUM_THREADS = 64 + 32 * SPL_WARPS + 32 * EPI_WARPS;   // 448
 constexpr int EPI_STG_BYTES = 32 * 16 * 4;        // per-warp 32 x 16 staging tile, 64 B rows, XOR-swizzled 16 B chunks
 constexpr int OFF_BARS = STAGES * STAGE_BYTES;
 constexpr int OFF_SCHED = OFF_BARS + 256;
-constexpr int OFF_STG = OFF_SCHED + 256;
+constexpr int OFF_STG = OFF_SCHED + 512;
 constexpr int SMEM_BYTES = OFF_STG + EPI_WARPS * EPI_STG_BYTES + 1024 /*align slack*/;
 constexpr int TMEM_COLS = 512;
 constexpr uint32_t ACC_MAIN = 0, ACC_X = 128, A_BASE = 256, A_STAGE_COLS = 64;
 
-constexpr int MAXP = 4;
+constexpr int MAXP = kTc3MaxProblems;   // 16: e.g. the 5 layers x 3 bond types of a message MLP as one dependent chain
 
 // instruction descriptor, kind::tf32: D = F32 (bits 4-5 = 1), A/B = TF32 (bits 7-9, 10-12 = 2), N >> 3 at bits 17-22,
 // M >> 4 at bits 24-28; bit 16 = B is MN-major (TN mode).  A comes from TMEM (always K-major, bit 15 = 0).
@@ -80,6 +80,12 @@ struct Params {
   int tn_mt[MAXP];          // TN: ceil(Nn / 128)
   int tn_nn[MAXP];          // TN: Nn
   float* bias_part[MAXP];   // TN: [splits][Nn] partial column sums of G (nullptr: not wanted)
+  // dependent chains (NT): problem p reads as its A operand what problem dep[p] writes (the next layer of an MLP);
+  // a tile of p at row block i may start once all n_tiles[dep[p]] tiles of row block i of dep[p] are stored.
+  // flags[flag_off[p] + i] counts the stored tiles of row block i of problem p (zeroed by the host before the launch).
+  int dep[MAXP];
+  int flag_off[MAXP];
+  int* flags;
   int nprob;
   int chunk_rows;           // TN: reduction rows per work item (multiple of 32)
   int diag;                 // timing experiments (gib_tc_debug >> 8; results are wrong with most of them):
@@ -150,6 +156,20 @@ __device__ __forceinline__ float lds32(uint32_t saddr) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr) : "memory");
   return v;
+}
+
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// chain hand-off: all 8 epilogue warps have stored their part of the tile -> one release increment of the row
+// block's counter (named barrier 1 = the 256 epilogue threads)
+__device__ __forceinline__ void signal_tile(int* flag) {
+  fence_proxy_async_all();
+  __threadfence();
+  asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+  if (threadIdx.x == 32 * (2 + SPL_WARPS)) {
+    __threadfence();
+    atomicAdd(flag, 1);
+  }
 }
 
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
@@ -237,6 +257,23 @@ tc3_gemm_kernel(const __grid_constant__ Maps maps, const Params P) {
         const CUtensorMap* map_a = &maps.a[w.p];
         const CUtensorMap* map_b = &maps.b[w.p];
         const int base = S.base[w.p];
+        if constexpr (!TN) {
+          if (P.flags && P.dep[w.p] >= 0) {       // chain: the row block of the layer below must be complete
+            const int d = P.dep[w.p];
+            const int* f = P.flags + P.flag_off[d] + w.m0 / BM;
+            const int need = P.n_tiles[d];
+            const long long t0 = clock64();
+            int have;
+            do {
+              asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(have) : "l"(f) : "memory");
+              if (have < need) {
+                __nanosleep(64);
+                if (clock64() - t0 > 20000000000LL) __trap();   // ~10 s: a dead-lock, not contention
+              }
+            } while (have < need);
+            fence_proxy_async_all();               // other SMs' generic-proxy stores -> this SM's async-proxy (TMA) reads
+          }
+        }
         const int rot = (P.diag & DG_ROTATE) ? (int)(blockIdx.x % (unsigned)w.nkb) : 0;
         for (int kb0 = 0; kb0 < w.nkb; ++kb0) {
           const int kb = (kb0 + rot) % w.nkb;
@@ -444,10 +481,10 @@ tc3_gemm_kernel(const __grid_constant__ Maps maps, const Params P) {
         }
         tc_fence_before();
         mbar_arrive(acc_empty);                  // the MMA warp may overwrite the accumulators now
-        if (P.diag & DG_NO_EPI) continue;
         const float* const bias = g.bias;
 #pragma unroll
         for (int chunk = 0; chunk < 4; ++chunk) {
+          if (P.diag & DG_NO_EPI) break;
           __syncwarp();
           // lane = tile row; 16-byte chunk j of row `lane` is stored at chunk (j ^ ((lane >> 1) & 3)): 8 consecutive
           // rows hit 8 distinct bank groups on the write, and the 2 rows x 4 chunks of a read phase do as well
@@ -555,6 +592,8 @@ tc3_gemm_kernel(const __grid_constant__ Maps maps, const Params P) {
         tc_fence_before();
         mbar_arrive(acc_empty);
       }
+      if constexpr (!TN)
+        if (P.flags) signal_tile(P.flags + P.flag_off[w.p] + w.m0 / BM);
     }
   }
 
@@ -748,10 +787,10 @@ bool tc3_eligible(const GemmNT& p) {
          p.B_lo && al(p.A) && al(p.B_hi) && al(p.B_lo);
 }
 
-// up to MAXP independent NT problems in one persistent launch (weights as pre-split TF32 planes)
-int gemm_nt_tc3_group(const GemmNT* ps, int n, cudaStream_t st) {
+// up to MAXP NT problems in one persistent launch (weights as pre-split TF32 planes); dep == nullptr: independent
+static int launch_nt(const GemmNT* ps, const int* dep, int n, int* flags, cudaStream_t st) {
   using namespace tc3;
-  if (n < 1 || n > MAXP) { set_error("gemm_nt_tc3_group: %d problems (max %d)", n, MAXP); return -2; }
+  if (n < 1 || n > MAXP) { set_error("gemm_nt_tc3: %d problems (max %d)", n, MAXP); return -2; }
   int num_sms = 0;
   GIB_TRY(prepare(&num_sms));
   Maps maps;
@@ -761,8 +800,11 @@ int gemm_nt_tc3_group(const GemmNT* ps, int n, cudaStream_t st) {
   long long tiles = 0;
   int np = 0;
   int spec = -1;
+  int slot[MAXP];                 // input index -> launch slot (-1: skipped, no rows)
+  int flag_ints = 0;
   for (int i = 0; i < n; ++i) {
     const GemmNT& p = ps[i];
+    slot[i] = -1;
     if (p.M <= 0 || p.N <= 0) continue;
     if (!tc3_eligible(p)) { set_error("gemm_nt_tc3: operands violate the TMA alignment / pre-split contract"); return -2; }
     const int sp = epi_spec(p);
@@ -773,6 +815,19 @@ int gemm_nt_tc3_group(const GemmNT* ps, int n, cudaStream_t st) {
     P.g[np] = p;
     P.n_tiles[np] = ceil_div(p.N, BN);
     P.k_blocks[np] = ceil_div(p.K, BKF);
+    P.dep[np] = -1;
+    P.flag_off[np] = flag_ints;
+    flag_ints += ceil_div(p.M, BM) + 1;                         // row blocks of the (capacity) row count
+    if (dep && dep[i] >= 0) {
+      if (dep[i] >= i || slot[dep[i]] < 0) { set_error("gemm_nt_tc3_chain: problem %d depends on %d", i, dep[i]); return -2; }
+      const GemmNT& d = ps[dep[i]];
+      if (d.M != p.M || d.m_dev != p.m_dev || d.base_dev != p.base_dev || d.C != p.A) {
+        set_error("gemm_nt_tc3_chain: problem %d does not consume the rows problem %d produces", i, dep[i]);
+        return -2;
+      }
+      P.dep[np] = slot[dep[i]];
+    }
+    slot[i] = np;
     tiles += (long long)ceil_div(p.M, BM) * P.n_tiles[np];      // upper bound when the row count lives on the device
     work += p.work > 0 ? p.work : 2.0 * p.M * (double)p.N * p.K;
     ++np;
@@ -780,6 +835,10 @@ int gemm_nt_tc3_group(const GemmNT* ps, int n, cudaStream_t st) {
   if (np == 0) return 0;
   P.nprob = np;
   P.diag = g_tc_debug >> 8;
+  if (dep) {
+    P.flags = flags;
+    GIB_CUDA_TRY(cudaMemsetAsync(flags, 0, (size_t)flag_ints * sizeof(int), st));
+  }
   const int grid = (int)(tiles < num_sms ? tiles : num_sms);
   ProfScope prof(PROF_GEMM_NT, work, st);
   switch (spec) {
@@ -791,6 +850,19 @@ int gemm_nt_tc3_group(const GemmNT* ps, int n, cudaStream_t st) {
   }
   GIB_LAUNCH_CHECK();
   return 0;
+}
+
+int gemm_nt_tc3_group(const GemmNT* ps, int n, cudaStream_t st) { return launch_nt(ps, nullptr, n, nullptr, st); }
+
+size_t tc3_chain_flag_ints(const GemmNT* ps, int n) {
+  size_t f = 0;
+  for (int i = 0; i < n; ++i) f += (size_t)ceil_div(ps[i].M > 0 ? ps[i].M : 0, tc3::BM) + 1;
+  return f;
+}
+
+int gemm_nt_tc3_chain(const GemmNT* ps, const int* dep, int n, int* flags, cudaStream_t st) {
+  if (!flags) { set_error("gemm_nt_tc3_chain: no flag buffer"); return -2; }
+  return launch_nt(ps, dep, n, flags, st);
 }
 
 // ---- weight gradients --------------------------------------------------------------------------------------------
@@ -815,6 +887,8 @@ void tc3_dw_layout(const GemmDW* qs, int n, long long plan_rows, Dw3Layout* L) {
   long long c = ceil_div_ll(rows * max_tiles, num_sms);
   c = ceil_div_ll(c, BKF) * BKF;
   if (c < 8 * BKF) c = 8 * BKF;                       // >= 256 reduction rows per item: amortise the 64 KB tile drain
+  if (c > 32 * BKF) c = 32 * BKF;                     // <= 1024: the tensor core accumulates with truncation, keep the
+                                                      // chains in one accumulator short (more items than SMs is fine)
   L->chunk_rows = (int)c;
   size_t off = 0;
   for (int i = 0; i < MAXP; ++i) {

@@ -172,6 +172,9 @@ struct Bump {
   }
 };
 
+// counters of one dependent-chain launch: <= kTc3MaxProblems problems x (row blocks + 1)
+static size_t chain_flag_floats(size_t max_rows) { return (size_t)kTc3MaxProblems * (max_rows / 128 + 2); }
+
 static void mlp_act_layout(const Plan& pl, const Mlp& m, size_t rows, Bump& bp, MlpAct& a, bool last_external) {
   for (int l = 1; l <= m.n; ++l) {
     const Lin& L = pl.lins[m.first + l - 1];
@@ -290,6 +293,7 @@ int make_run(const gib_dims& d, const int* hdr, Run& r) {
   mlp_act_layout(pl, pl.fconn2, B, bp, L.fconn2, true);
   L.fterm2.ld[0] = Gp;
   mlp_act_layout(pl, pl.fterm2, B, bp, L.fterm2, true);
+  L.flags = bp.take(chain_flag_floats(std::max(std::max(S, P), std::max(B, (size_t)r.E))));
   L.total = bp.off;
   return 0;
 }
@@ -382,6 +386,7 @@ struct MlpBwdJob {
   const float* Gtop; float* dX0; int ld_dx; const float* dx_aux;
   const int* m_dev = nullptr; const int* base_dev = nullptr;
 };
+static int* fwd_flags(const Run& r) { return reinterpret_cast<int*>(r.ws + r.L.flags); }
 static const int* type_count_dev(const Run& r, int g) { return r.cap ? r.dev_hdr + HDR_TYPE_COUNT + g : nullptr; }
 static const int* type_base_dev(const Run& r, int g) { return r.cap ? r.dev_hdr + HDR_TYPE_BASE + g : nullptr; }
 
@@ -391,7 +396,7 @@ static size_t mlp_max_ld(const Plan& pl, const Mlp& m) {
   return w;
 }
 
-static int mlp_forward_multi(const Run& r, const MlpJob* jobs, int n) {
+static int mlp_forward_multi(const Run& r, const MlpJob* jobs, int n, int* flags = nullptr) {
   bool same = n <= 4;
   for (int i = 1; i < n && same; ++i) same = jobs[i].m->n == jobs[0].m->n;
   if (!same) {
@@ -404,7 +409,11 @@ static int mlp_forward_multi(const Run& r, const MlpJob* jobs, int n) {
   }
   const float* x[4]; int ldx[4];
   for (int i = 0; i < n; ++i) { x[i] = jobs[i].X0 + (size_t)jobs[i].row0 * jobs[i].a->ld[0]; ldx[i] = jobs[i].a->ld[0]; }
-  for (int l = 1; l <= jobs[0].m->n; ++l) {
+  const int depth = jobs[0].m->n;
+  GemmNT all[kTc3MaxProblems];
+  int dep[kTc3MaxProblems], layer_of[kTc3MaxProblems], last[4] = {-1, -1, -1, -1}, nall = 0;
+  const bool try_chain = depth >= 2 && depth * n <= kTc3MaxProblems;
+  for (int l = 1; l <= depth; ++l) {
     GemmNT ps[4];
     int np = 0, idx[4];
     for (int i = 0; i < n; ++i) {
@@ -428,16 +437,43 @@ static int mlp_forward_multi(const Run& r, const MlpJob* jobs, int n) {
       if (ldx[i] < L.Cp) { set_error("mlp_forward_multi: input ld %d < padded K %d", ldx[i], L.Cp); return -2; }
       idx[np++] = i;
     }
-    GIB_TRY(gemm_nt_group(ps, np, r.st));
+    if (try_chain) {       // collect: the layers of all members become ONE dependent-chain launch below
+      for (int k = 0; k < np; ++k) {
+        all[nall] = ps[k];
+        dep[nall] = last[idx[k]];
+        layer_of[nall] = l;
+        last[idx[k]] = nall++;
+      }
+    } else {
+      GIB_TRY(gemm_nt_group(ps, np, r.st));
+    }
     for (int k = 0; k < np; ++k) { x[idx[k]] = ps[k].C; ldx[idx[k]] = ps[k].ldc; }
+  }
+  if (try_chain && nall) {
+    if (flags && gemm_nt_chain_ok(all, nall)) return gemm_nt_chain(all, dep, nall, flags, r.st);
+    // not eligible as a chain (tiny / unaligned members, tensor cores off): layer by layer (members of a layer are
+    // contiguous in `all`)
+    for (int k0 = 0; k0 < nall;) {
+      int k1 = k0 + 1;
+      while (k1 < nall && layer_of[k1] == layer_of[k0]) ++k1;
+      GIB_TRY(gemm_nt_group(all + k0, k1 - k0, r.st));
+      k0 = k1;
+    }
   }
   return 0;
 }
 
+// Backward of sibling MLPs of equal depth.  Three launches' worth of structure instead of three per layer:
+//   (A) the input-gradient GEMMs of layers n..2 (G_{l-1} = (G_l W_l) . selu'(X_{l-1})) as ONE dependent chain,
+//       every G_l kept in its own buffer;
+//   (B) the weight gradients of ALL layers and members (dW_l = G_l^T X_{l-1}) as ONE grouped launch + ONE reduction;
+//   (C) the first layer's input gradient (if wanted).
+// plan_rows: expected total rows of the members of ONE layer (capacity mode: the entry capacity), 0 = their sum.
 static int mlp_backward_multi(const Run& r, const BwdBufs& bb, const MlpBwdJob* jobs, int n, long long plan_rows = 0) {
   bool same = n <= 4;
   for (int i = 1; i < n && same; ++i) same = jobs[i].m->n == jobs[0].m->n;
-  if (!same) {
+  const int depth = jobs[0].m->n;
+  if (!same || depth > 8 || depth * n > kTc3MaxProblems) {
     for (int i = 0; i < n; ++i) {
       if (jobs[i].m_dev) { set_error("mlp_backward_multi: device-side row counts need MLPs of equal depth"); return -2; }
       GIB_TRY(mlp_backward(r, bb, *jobs[i].m, jobs[i].X0, *jobs[i].a, jobs[i].row0, jobs[i].rows, jobs[i].Gtop,
@@ -445,72 +481,94 @@ static int mlp_backward_multi(const Run& r, const BwdBufs& bb, const MlpBwdJob* 
     }
     return 0;
   }
-  const float* G[4]; float* ping[4]; float* pong[4];
+  // G[l][i]: gradient w.r.t. the pre-activation of layer l of member i; G[depth] = the caller's Gtop
+  const float* G[9][4];
   size_t off = 0;
-  for (int i = 0; i < n; ++i) {   // private ping/pong slice per job inside GA / GB
-    G[i] = jobs[i].Gtop;
-    ping[i] = r.scratch + bb.GA + off;
-    pong[i] = r.scratch + bb.GB + off;
+  for (int i = 0; i < n; ++i) {
+    G[depth][i] = jobs[i].Gtop;
+    for (int l = 1; l < depth; ++l) G[l][i] = r.scratch + bb.Gl[l] + off;
     // capacity mode: the members' live row ranges are disjoint parts of ONE buffer of `rows` rows -> shared slice
     if (!jobs[i].m_dev) off += ((size_t)std::max(jobs[i].rows, 0) * mlp_max_ld(r.pl, *jobs[i].m) + 31) & ~(size_t)31;
   }
-  for (int l = jobs[0].m->n; l >= 1; --l) {
-    GemmNT ps[4];
-    GemmDW qs[4];
-    int np = 0, nq = 0, idx[4];
+  auto x_in = [&](const MlpBwdJob& j, int l, int* ld) -> const float* {   // input activations of layer l
+    *ld = j.a->ld[l - 1];
+    return (l == 1) ? j.X0 + (size_t)j.row0 * j.a->ld[0] : r.ws + j.a->y[l - 1] + (size_t)j.row0 * j.a->ld[l - 1];
+  };
+  // ---- (A) input gradients of layers depth..2 ------------------------------------------------------------------
+  GemmNT all[kTc3MaxProblems];
+  int dep[kTc3MaxProblems], layer_of[kTc3MaxProblems], last[4] = {-1, -1, -1, -1}, nall = 0;
+  for (int l = depth; l >= 2; --l)
     for (int i = 0; i < n; ++i) {
       const MlpBwdJob& j = jobs[i];
       if (j.rows <= 0) continue;
       const Lin& L = r.pl.lins[j.m->first + l - 1];
-      const float* Xin = (l == 1) ? j.X0 + (size_t)j.row0 * j.a->ld[0]
-                                  : r.ws + j.a->y[l - 1] + (size_t)j.row0 * j.a->ld[l - 1];
-      const int ldxin = j.a->ld[l - 1];
+      int ldxin;
+      const float* Xin = x_in(j, l, &ldxin);
+      GemmNT& p = all[nall];
+      p = GemmNT();
+      p.A = G[l][i]; p.lda = L.Rp; p.B = r.packed + L.owt; p.ldb = L.Rp;
+      p.B_hi = r.packed + L.owt_hi; p.B_lo = r.packed + L.owt_lo;
+      p.M = j.rows; p.N = L.Ctp; p.K = L.Rp; p.n_store = L.Ctp; p.n_valid = L.Ctp;
+      p.work = 2.0 * j.rows * (double)L.R * L.Ct;
+      p.C = const_cast<float*>(G[l - 1][i]); p.ldc = L.Ctp;
+      p.mode = EPI_MUL_DACT; p.act = j.m->act; p.aux = Xin; p.ldaux = ldxin;
+      p.m_dev = j.m_dev; p.base_dev = j.base_dev;
+      dep[nall] = last[i];
+      layer_of[nall] = l;
+      last[i] = nall++;
+    }
+  if (nall) {
+    if (nall >= 2 && gemm_nt_chain_ok(all, nall)) {
+      GIB_TRY(gemm_nt_chain(all, dep, nall, reinterpret_cast<int*>(r.scratch + bb.flags), r.st));
+    } else {
+      for (int k0 = 0; k0 < nall;) {
+        int k1 = k0 + 1;
+        while (k1 < nall && layer_of[k1] == layer_of[k0]) ++k1;
+        GIB_TRY(gemm_nt_group(all + k0, k1 - k0, r.st));
+        k0 = k1;
+      }
+    }
+  }
+  // ---- (C) input gradient of the first layer (may chain through a shared buffer via aux: keep the members in order)
+  for (int i = 0; i < n; ++i) {
+    const MlpBwdJob& j = jobs[i];
+    if (j.rows <= 0 || !j.dX0) continue;
+    const Lin& L = r.pl.lins[j.m->first];
+    GemmNT p1;
+    p1.A = G[1][i]; p1.lda = L.Rp; p1.B = r.packed + L.owt; p1.ldb = L.Rp;
+    p1.B_hi = r.packed + L.owt_hi; p1.B_lo = r.packed + L.owt_lo;
+    p1.M = j.rows; p1.N = L.Ctp; p1.K = L.Rp; p1.n_store = L.Ctp; p1.n_valid = L.Ctp;
+    p1.work = 2.0 * j.rows * (double)L.R * L.Ct;
+    p1.C = j.dX0; p1.ldc = j.ld_dx;
+    p1.m_dev = j.m_dev; p1.base_dev = j.base_dev;
+    if (j.dx_aux) { p1.mode = EPI_ADD; p1.aux = j.dx_aux; p1.ldaux = j.ld_dx; }
+    else { p1.mode = EPI_ACT; p1.act = ACT_NONE; p1.bias = nullptr; }
+    GIB_TRY(gemm_nt(p1, r.st));
+  }
+  // ---- (B) weight gradients of every layer and member: one grouped launch + one reduction -----------------------
+  GemmDW qs[kTc3MaxProblems];
+  int nq = 0;
+  for (int l = depth; l >= 1; --l)
+    for (int i = 0; i < n; ++i) {
+      const MlpBwdJob& j = jobs[i];
+      if (j.rows <= 0) continue;
+      const Lin& L = r.pl.lins[j.m->first + l - 1];
+      int ldxin;
+      const float* Xin = x_in(j, l, &ldxin);
       GemmDW& q = qs[nq++];
       q = GemmDW();
-      q.G = G[i]; q.ldg = L.Rp; q.Nn = L.Rp; q.X = Xin; q.ldx = ldxin; q.Kk = L.Cp; q.M = j.rows;
+      q.G = G[l][i]; q.ldg = L.Rp; q.Nn = L.Rp; q.X = Xin; q.ldx = ldxin; q.Kk = L.Cp; q.M = j.rows;
       q.dW = r.grads[L.pw] + L.src_off;
       q.dbias = L.pb >= 0 ? r.grads[L.pb] : nullptr;
       q.R = L.R; q.C = L.C; q.Rb = L.Rb; q.Rbp = L.Rbp; q.rs = L.rs; q.cs = L.cs;
       q.scratch = r.scratch + bb.dw; q.half_floats = bb.dw_half;
       q.work = 2.0 * j.rows * (double)L.R * L.C;
       q.m_dev = j.m_dev; q.base_dev = j.base_dev;
-      if (l > 1) {
-        GemmNT& p = ps[np];
-        p = GemmNT();
-        p.A = G[i]; p.lda = L.Rp; p.B = r.packed + L.owt; p.ldb = L.Rp;
-        p.B_hi = r.packed + L.owt_hi; p.B_lo = r.packed + L.owt_lo;
-        p.M = j.rows; p.N = L.Ctp; p.K = L.Rp; p.n_store = L.Ctp; p.n_valid = L.Ctp;
-        p.work = 2.0 * j.rows * (double)L.R * L.Ct;
-        p.C = (G[i] == ping[i]) ? pong[i] : ping[i]; p.ldc = L.Ctp;
-        p.mode = EPI_MUL_DACT; p.act = j.m->act; p.aux = Xin; p.ldaux = ldxin;
-        p.m_dev = j.m_dev; p.base_dev = j.base_dev;
-        idx[np++] = i;
-      }
     }
-    GIB_TRY(gemm_dw_group(qs, nq, plan_rows, r.st));   // one grouped launch for the layer's weight gradients
-    if (l == 1) {
-      for (int i = 0; i < n; ++i) {   // input gradients may chain through a shared buffer (aux): keep them in order
-        const MlpBwdJob& j = jobs[i];
-        if (j.rows <= 0 || !j.dX0) continue;
-        const Lin& L = r.pl.lins[j.m->first];
-        GemmNT p1;
-        p1.A = G[i]; p1.lda = L.Rp; p1.B = r.packed + L.owt; p1.ldb = L.Rp;
-        p1.B_hi = r.packed + L.owt_hi; p1.B_lo = r.packed + L.owt_lo;
-        p1.M = j.rows; p1.N = L.Ctp; p1.K = L.Rp; p1.n_store = L.Ctp; p1.n_valid = L.Ctp;
-        p1.work = 2.0 * j.rows * (double)L.R * L.Ct;
-        p1.C = j.dX0; p1.ldc = j.ld_dx;
-        p1.m_dev = j.m_dev; p1.base_dev = j.base_dev;
-        if (j.dx_aux) { p1.mode = EPI_ADD; p1.aux = j.dx_aux; p1.ldaux = j.ld_dx; }
-        else { p1.mode = EPI_ACT; p1.act = ACT_NONE; p1.bias = nullptr; }
-        GIB_TRY(gemm_nt(p1, r.st));
-      }
-    }
-    if (np) {
-      GIB_TRY(gemm_nt_group(ps, np, r.st));
-      for (int k = 0; k < np; ++k) G[idx[k]] = ps[k].C;
-    }
-  }
-  if (jobs[0].m->n == 1) GIB_TRY(dw_join(r.st));   // see mlp_backward
+  GIB_TRY(gemm_dw_group(qs, nq, plan_rows * depth, r.st));
+  // the side-stream reduction reads only its scratch half; a first-generation / SIMT fallback job may still read
+  // the caller's Gtop buffer: finish it before returning
+  if (!(g_use_tc && (g_tc_debug & 1) == 0)) GIB_TRY(dw_join(r.st));
   return 0;
 }
 
@@ -533,7 +591,7 @@ static int readout_forward(const Run& r, float* out) {
     {   // att_nn(cat) and emb_nn(hidden) are independent: one grouped launch per layer
       MlpJob jobs[2] = {{&pl.gatt, r.ws + L.cat_att, &L.gatt, 0, (int)S, nullptr, 0, 0},
                         {&pl.gemb, hT, &L.gemb, 0, (int)S, nullptr, 0, 0}};
-      GIB_TRY(mlp_forward_multi(r, jobs, 2));
+      GIB_TRY(mlp_forward_multi(r, jobs, 2, fwd_flags(r)));
     }
     GIB_TRY(graph_gather_fwd(r.ws + L.g, r.ws + L.attn, r.ws + L.gatt.y[pl.gatt.n], r.ws + L.gemb.y[pl.gemb.n], Gp,
                              r.ga.dst_ptr, d.N, d.B, d.big, r.st));                   // modules.py:47-52
@@ -541,7 +599,7 @@ static int readout_forward(const Run& r, float* out) {
   {   // modules.py:250-251: the two tier-1 heads share their input
     MlpJob jobs[2] = {{&pl.fadd1, hT, &L.fadd1, 0, (int)S, nullptr, 0, 0},
                       {&pl.fconn1, hT, &L.fconn1, 0, (int)S, nullptr, 0, 0}};
-    GIB_TRY(mlp_forward_multi(r, jobs, 2));
+    GIB_TRY(mlp_forward_multi(r, jobs, 2, fwd_flags(r)));
   }
   GIB_TRY(concat_flat(r.ws + L.cat_add, L.fadd2.ld[0], r.ws + L.fadd1.y[pl.fadd1.n], L.fadd1.ld[pl.fadd1.n], d.N,
                       d.f_add, r.ws + L.g, Gp, pl.G, d.B, r.st));
@@ -552,7 +610,7 @@ static int readout_forward(const Run& r, float* out) {
     MlpJob jobs[3] = {{&pl.fadd2, r.ws + L.cat_add, &L.fadd2, 0, d.B, out, pl.apd, na},
                       {&pl.fconn2, r.ws + L.cat_conn, &L.fconn2, 0, d.B, out + na, pl.apd, nc},
                       {&pl.fterm2, r.ws + L.g, &L.fterm2, 0, d.B, out + na + nc, pl.apd, 1}};
-    GIB_TRY(mlp_forward_multi(r, jobs, 3));
+    GIB_TRY(mlp_forward_multi(r, jobs, 3, fwd_flags(r)));
   }
   return 0;
 }
@@ -648,12 +706,12 @@ static int node_model_forward(const Run& r, float* out) {
       for (int g = 0; g < r.ngroups; ++g)
         jobs[g] = MlpJob{&pl.msg[g], r.ws + L.x0[t], &L.msg[t], r.tb[g], r.tc[g], nullptr, 0, 0,
                          type_count_dev(r, g), type_base_dev(r, g)};
-      GIB_TRY(mlp_forward_multi(r, jobs, r.ngroups));
+      GIB_TRY(mlp_forward_multi(r, jobs, r.ngroups, fwd_flags(r)));
       if (d.model == GIB_ATTGGNN) {
         for (int g = 0; g < r.ngroups; ++g)
           jobs[g] = MlpJob{&pl.att[g], r.ws + L.x0[t], &L.att[t], r.tb[g], r.tc[g], nullptr, 0, 0,
                            type_count_dev(r, g), type_base_dev(r, g)};
-        GIB_TRY(mlp_forward_multi(r, jobs, r.ngroups));
+        GIB_TRY(mlp_forward_multi(r, jobs, r.ngroups, fwd_flags(r)));
       }
     }
     const float* msgs = r.ws + L.msg[t].y[pl.msg[0].n];
@@ -876,17 +934,18 @@ static void mlp_extent(const Plan& pl, const Mlp& m, size_t rows, size_t& big, s
 static void group_extent(const Plan& pl, const Mlp* const* ms, const size_t* rows, int n, long long plan_rows, size_t& dw) {
   for (int i = 1; i < n; ++i)
     if (ms[i]->n != ms[0]->n) return;
-  for (int l = 0; l < ms[0]->n; ++l) {
-    GemmDW qs[4];
-    int nq = 0;
-    for (int i = 0; i < n && nq < 4; ++i) {
+  const int depth = ms[0]->n;
+  if (depth * n > kTc3MaxProblems) return;
+  GemmDW qs[kTc3MaxProblems];     // all layers of all members: one grouped launch (mlp_backward_multi)
+  int nq = 0;
+  for (int l = 0; l < depth; ++l)
+    for (int i = 0; i < n; ++i) {
       if (rows[i] == 0) continue;
       const Lin& L = pl.lins[ms[i]->first + l];
       qs[nq].M = (int)rows[i]; qs[nq].Nn = L.Rp; qs[nq].Kk = L.Cp;
       ++nq;
     }
-    if (nq) dw = std::max(dw, 2 * gemm_dw_group_half_floats(qs, nq, plan_rows));
-  }
+  if (nq) dw = std::max(dw, 2 * gemm_dw_group_half_floats(qs, nq, plan_rows * depth));
 }
 
 void make_bwd(const Run& r, BwdBufs& bb) {
@@ -956,7 +1015,17 @@ void make_bwd(const Run& r, BwdBufs& bb) {
     if (d.model != GIB_MNN) big = std::max(big, S * (mlp_max_ld(pl, pl.gatt) + mlp_max_ld(pl, pl.gemb)) + 64);
   }
   Bump bp;
-  bb.GA = bp.take(big); bb.GB = bp.take(big); bb.T1 = bp.take(big); bb.T2 = bp.take(big);
+  int max_depth = 2;
+  {
+    const Mlp* every[] = {&pl.msg[0], &pl.att[0], &pl.gatt, &pl.gemb, &pl.fadd1, &pl.fconn1, &pl.fadd2, &pl.fconn2,
+                          &pl.fterm2, &pl.embnn, &pl.emsg, &pl.eatt};
+    for (const Mlp* m : every) max_depth = std::max(max_depth, std::min(m->n, 8));
+  }
+  for (int l = 0; l < 8; ++l) bb.Gl[l] = 0;
+  for (int l = 1; l < std::max(max_depth, 3); ++l) bb.Gl[l] = bp.take(big);   // one gradient buffer per layer (chains)
+  bb.GA = bb.Gl[1]; bb.GB = bb.Gl[2];                                         // ping / pong of the single-MLP path
+  bb.T1 = bp.take(big); bb.T2 = bp.take(big);
+  bb.flags = bp.take(chain_flag_floats(std::max(std::max(S, P), std::max(B, E))));
   bb.dw = bp.take(dw);
   bb.dw_half = dw / 2;          // gemm_dw alternates between two halves (helper side stream)
   bb.dh = bp.take(S * Hp); bb.dh2 = bp.take(S * Hp);

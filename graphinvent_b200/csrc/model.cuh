@@ -57,6 +57,7 @@ struct Layout {
   // readout
   size_t hfinal, cat_att, attn, g, cat_add, cat_conn;
   MlpAct gatt, gemb, fadd1, fconn1, fadd2, fconn2, fterm2;
+  size_t flags;     // row-block counters of the dependent-chain GEMM launches (ints, zeroed per launch)
   size_t total;
 };
 
@@ -64,6 +65,8 @@ struct BwdBufs {
   size_t dw_half;
   size_t GA, GB, T1, T2, dw, dh, dh2, dmsum, dgi, dgh, dx0, dcat_att, dcat_add, dcat_conn, dgterm, dg;
   size_t dmem, dmem2, dEMx, dENx, dEMm, dENm, st3;
+  size_t Gl[8];     // per-layer gradient buffers of a chained MLP backward (Gl[0] unused)
+  size_t flags;
   size_t total;
 };
 

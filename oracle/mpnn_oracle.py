@@ -83,6 +83,31 @@ def make_constants(model="GGNN", **kw):
 MARGINS = None
 
 
+# SELU-kink probe (tests only).  KINK = (tau, side): the derivative of every SELU whose input lies within tau of 0 is
+# forced to its right ('R': scale) or left ('L': scale*alpha) limit in the backward pass; the forward values are
+# untouched (SELU is continuous).  The difference between the two fp64 gradients is the total effect the units
+# inside the band can have on a gradient -- what two correct fp32 evaluations may legitimately disagree by when their
+# rounding noise puts some of those inputs on different sides of 0.
+KINK = None
+_SELU_SCALE, _SELU_ALPHA = 1.0507009873554804934193349852946, 1.6732632423543772848170429916717
+
+
+class _SeluKink(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, tau, side):
+        ctx.save_for_backward(x)
+        ctx.tau, ctx.side = tau, side
+        return F.selu(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        d = torch.where(x > 0, torch.full_like(x, _SELU_SCALE), _SELU_SCALE * _SELU_ALPHA * torch.exp(x))
+        forced = _SELU_SCALE if ctx.side == "R" else _SELU_SCALE * _SELU_ALPHA
+        d = torch.where(x.abs() < ctx.tau, torch.full_like(x, forced), d)
+        return g * d, None, None
+
+
 def mlp(sd, prefix, x):
     """gnn/modules.py:111-170 -- Linear -> SELU (-> AlphaDropout(p=0) == identity)
     for every layer INCLUDING the last; Linear layers sit at seq.0, seq.3, ..."""
@@ -91,7 +116,7 @@ def mlp(sd, prefix, x):
         pre = F.linear(x, sd[f"{prefix}.seq.{i}.weight"], sd[f"{prefix}.seq.{i}.bias"])
         if MARGINS is not None and pre.numel():
             MARGINS.append(float(pre.detach().abs().min()))
-        x = F.selu(pre)
+        x = F.selu(pre) if KINK is None else _SeluKink.apply(pre, KINK[0], KINK[1])
         i += 3
     return x
 

@@ -368,22 +368,42 @@ def test_full_size_properties(cfg):
 
 
 # ------------------------------------------------------------------------------------------
-# fp64-anchored parity on ARBITRARY batches (no oracle-selected inputs): the yardstick is the reference's own
-# fp32 rounding, measured as the distance between the fp32 and the fp64 evaluation of the same expression.
-#   gradients, per tensor:  ||g_cuda - g_fp64|| <= C * ||g_ref32 - g_fp64|| + 1e-6 ||g_fp64|| + 1e-7 max_k ||g_fp64_k||
-#   logits, per molecule:   max|o_cuda - o_fp64| <= C * max|o_ref32 - o_fp64| + 1e-4
+# fp64-anchored parity on ARBITRARY batches (no oracle-selected inputs).  The yardstick is the reference's own fp32
+# rounding -- the distance between the fp32 and the fp64 evaluation of the same expression -- plus the one thing
+# rounding noise can legitimately change by more than noise: the side of 0 a SELU input falls on (SELU' jumps from
+# 1.758 to 1.051 there).  That effect is COMPUTED, not assumed: the fp64 oracle is differentiated twice with the
+# derivative of every SELU whose input lies within tau of 0 forced to its left / right limit (oracle KINK probe);
+# ||g_L - g_R|| is the total gradient change the units inside the band can cause.  tau = a few times the forward
+# rounding noise of the path (tensor cores: 3xTF32 products accumulate with truncation, measured logit deviation
+# ~1e-5; fp32 SIMT GEMMs: ~5e-6).
+#   gradients, per tensor:  ||g_cuda - g_fp64|| <= 2 ||g_ref32 - g_fp64|| + ||g_L(tau) - g_R(tau)|| + 1e-6 ||g_fp64||
+#   logits, per molecule:   max|o_cuda - o_fp64| <= 3 max|o_ref32 - o_fp64| + 1e-4
 #   APD argmax:             identical to the fp32 reference wherever the reference's own top-2 gap exceeds its own
 #                           fp32-vs-fp64 movement on that molecule (bond-less molecules included)
+#   loss:                   |loss - loss_fp64| <= 3 |loss_ref32 - loss_fp64| + 1e-5 max(1, |loss|)
 # ------------------------------------------------------------------------------------------
 FP64_C = 3.0
-FP64_REL = 1e-4      # SURVEY.md 8c gradient tolerance (per tensor, relative), here measured against the fp64 truth
+KINK_TAU = {1: 3e-5, 0: 3e-6}      # tensor cores on / off
 
 
-def _fp64_anchored(C, sd, nodes, edges, target, tag):
+def _fp64_anchored(C, sd, nodes, edges, target, tag, tensor_cores=1):
     from oracle import mpnn_oracle as O
+    lib = Fn_lib()
     l32, o32, g32 = O.train_step_grads(sd, C, nodes, edges, target)
     l64, o64, g64 = O.train_step_grads(sd, C, nodes, edges, target, dtype=torch.float64)
-    out, loss, grads = _step(_build(C, sd), nodes, edges, target)
+    tau = KINK_TAU[tensor_cores]
+    try:
+        O.KINK = (tau, "L")
+        _, _, gL = O.train_step_grads(sd, C, nodes, edges, target, dtype=torch.float64)
+        O.KINK = (tau, "R")
+        _, _, gR = O.train_step_grads(sd, C, nodes, edges, target, dtype=torch.float64)
+    finally:
+        O.KINK = None
+    lib.gib_set_tensor_cores(tensor_cores)
+    try:
+        out, loss, grads = _step(_build(C, sd), nodes, edges, target)
+    finally:
+        lib.gib_set_tensor_cores(1)
     # logits
     e_ref = (o32.double() - o64).abs().max(1).values
     e_cuda = (out.double() - o64).abs().max(1).values
@@ -394,27 +414,35 @@ def _fp64_anchored(C, sd, nodes, edges, target, tag):
     same = out.argmax(1) == o32.argmax(1)
     # gradients
     gscale = max(g.norm().item() for g in g64.values())
-    worst = ("", 0.0, 0.0, 0.0)
+    worst = ("", 0.0, 0.0, 0.0, 0.0)
+    tot = [0.0, 0.0, 0.0, 0.0]
     for k, g in g64.items():
         d_cuda = (grads[k].double() - g).norm().item()
         d_ref = (g32[k].double() - g).norm().item()
-        bound = FP64_C * d_ref + 1e-6 * g.norm().item() + 1e-7 * gscale
+        d_kink = (gL[k] - gR[k]).norm().item()
+        bound = 2.0 * d_ref + d_kink + 1e-6 * g.norm().item() + 1e-7 * gscale
+        for i, v in enumerate((d_cuda, d_ref, d_kink, g.norm().item())):
+            tot[i] += v * v
         if d_cuda / bound > worst[1]:
-            worst = (k, d_cuda / bound, d_cuda, d_ref)
+            worst = (k, d_cuda / bound, d_cuda, d_ref, d_kink)
+    tot = [t ** 0.5 for t in tot]
     bondless = edges.sum((1, 2, 3)) == 0
-    print(f"fp64-anchored [{tag}]: logits cuda-vs-fp64 {e_cuda.max().item():.2e} (ref32-vs-fp64 {e_ref.max().item():.2e}), "
-          f"decided rows {int(decided.sum())}/{len(decided)} (bond-less {int((decided & bondless).sum())}/{int(bondless.sum())}), "
-          f"worst gradient ratio {worst[1]:.2f} at {worst[0]} (cuda {worst[2]:.2e}, ref32 {worst[3]:.2e}), "
-          f"loss {loss:.7f} vs fp64 {float(l64):.7f} / fp32 {float(l32):.7f}")
+    print(f"fp64-anchored [{tag}, tensor cores {tensor_cores}]: logits cuda-vs-fp64 {e_cuda.max().item():.2e} (ref32-vs-fp64 "
+          f"{e_ref.max().item():.2e}), decided rows {int(decided.sum())}/{len(decided)} (bond-less "
+          f"{int((decided & bondless).sum())}/{int(bondless.sum())}); gradients, global L2: |g| {tot[3]:.3e}, cuda-fp64 {tot[0]:.2e}, "
+          f"ref32-fp64 {tot[1]:.2e}, kink band (tau {tau:g}) {tot[2]:.2e}; worst tensor {worst[0]}: {worst[1]:.2f} of its bound "
+          f"(cuda {worst[2]:.2e}, ref32 {worst[3]:.2e}, kink {worst[4]:.2e}); loss {loss:.7f} vs fp64 {float(l64):.7f} / fp32 {float(l32):.7f}")
     assert worst_row <= 0, f"logits: a molecule moves {worst_row + LOGIT_TOL:.3e} beyond {FP64_C} x the reference's own fp32 error"
     assert bool(same[decided].all()), f"argmax differs on {int((~same & decided).sum())} molecules the reference decides"
-    assert abs(loss - float(l64)) <= FP64_C * abs(float(l32) - float(l64)) + 1e-5
-    assert worst[1] <= 1.0, (f"gradient {worst[0]}: |cuda - fp64| = {worst[2]:.3e} exceeds {FP64_C} x |ref32 - fp64| = "
-                             f"{worst[3]:.3e} (+ floor)")
+    assert abs(loss - float(l64)) <= FP64_C * abs(float(l32) - float(l64)) + 1e-5 * max(1.0, abs(float(l64)))
+    assert worst[1] <= 1.0, (f"gradient {worst[0]}: |cuda - fp64| = {worst[2]:.3e} exceeds 2 x |ref32 - fp64| = {worst[3]:.3e} "
+                             f"+ kink band {worst[4]:.3e} (+ floor)")
+    assert tot[0] <= 2.0 * tot[1] + tot[2] + 1e-6 * tot[3]
 
 
+@pytest.mark.parametrize("tensor_cores", [1, 0])
 @pytest.mark.parametrize("model", MODELS)
-def test_fp64_anchored_default_dims_arbitrary_batch(model):
+def test_fp64_anchored_default_dims_arbitrary_batch(model, tensor_cores):
     from graphinvent_b200 import synthetic as S
     from oracle import mpnn_oracle as O
     C = O.make_constants(model)
@@ -427,7 +455,7 @@ def test_fp64_anchored_default_dims_arbitrary_batch(model):
     nodes = torch.from_numpy(np.concatenate([n2, n])).float()
     edges = torch.from_numpy(np.concatenate([e2, e])).float()
     target = torch.from_numpy(S.random_targets(nodes.shape[0], 625, seed=3))
-    _fp64_anchored(C, sd, nodes, edges, target, f"{model} default dims, 101 molecules incl. corner graphs")
+    _fp64_anchored(C, sd, nodes, edges, target, f"{model} default dims, 101 molecules incl. corner graphs", tensor_cores)
 
 
 def test_fp64_anchored_c2_slice():
