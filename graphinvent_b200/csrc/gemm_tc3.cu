@@ -91,10 +91,11 @@ struct Params {
   int diag;                 // timing experiments (gib_tc_debug >> 8; results are wrong with most of them):
                             //   1 no global stores   2 no epilogue after the drain   4 no split / STTM   8 no W_lo tile + MMAs
                             //   16 no MMAs   32 no TMA loads   64 no accumulator drain   128 rotate the k-block order per CTA
-                            //   256 interleave the MMAs of the two accumulators
+                            //   256 interleave the MMAs of the two accumulators   512 round-to-nearest activation split
+                            //   (results stay correct with 128, 256, 512)
 };
 enum { DG_NO_STORE = 1, DG_NO_EPI = 2, DG_NO_SPLIT = 4, DG_NO_BLO = 8, DG_NO_MMA = 16, DG_NO_TMA = 32, DG_NO_DRAIN = 64,
-       DG_ROTATE = 128, DG_INTERLEAVE = 256 };
+       DG_ROTATE = 128, DG_INTERLEAVE = 256, DG_RNA_SPLIT = 512 };
 
 struct Sched {              // computed once per CTA from host values or the device-side row counts
   int M[MAXP], base[MAXP], begin[MAXP + 1], splits[MAXP];
@@ -172,9 +173,23 @@ __device__ __forceinline__ void signal_tile(int* flag) {
   }
 }
 
+// round-to-nearest split (weights are split this way once per optimizer step, gib_model_pack): 7 ALU ops per element
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
   hi = to_tf32(x);
   lo = to_tf32(x - __uint_as_float(hi));
+}
+// truncation split for the activation operand: hi = the top 19 bits (what the tensor core reads anyway), lo = x - hi
+// (exact in fp32; the tensor core reads its top 19 bits): 2 ALU ops per element.  The splitter warps sit on the
+// critical path of every k-block and share their issue slots with two epilogue warps each -- with the 7-op split
+// they fell behind the MMAs whenever the epilogue was busy (profiles/r02_tc3_probe.md).  Error of the pair:
+// <= 2^-21 |x| instead of 2^-22 |x|, far below the tensor core's truncating accumulation.
+__device__ __forceinline__ void split_tf32_fast(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+template <bool RNA> __device__ __forceinline__ void split_act(float x, uint32_t& hi, uint32_t& lo) {
+  if (RNA) split_tf32(x, hi, lo);
+  else split_tf32_fast(x, hi, lo);
 }
 
 // EPI: epilogue specialisation shared by every problem of the launch.  The per-element epilogue must stay a few
@@ -359,6 +374,7 @@ tc3_gemm_kernel(const __grid_constant__ Maps maps, const Params P) {
     const int r = quarter * 32 + lane;                  // tile row (NT) / G column (TN) this thread owns
     const int t = threadIdx.x - 64;                     // 0..127 (TN: work split of the X tile)
     const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + A_BASE;
+    const bool rna = (P.diag & DG_RNA_SPLIT) != 0;
     int stage = 0;
     uint32_t phase = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
@@ -380,10 +396,13 @@ tc3_gemm_kernel(const __grid_constant__ Maps maps, const Params P) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 v = lds128(rowaddr + (((uint32_t)j ^ ((uint32_t)r & 7u)) << 4));
-            split_tf32(v.x, hi[4 * j + 0], lo[4 * j + 0]);
-            split_tf32(v.y, hi[4 * j + 1], lo[4 * j + 1]);
-            split_tf32(v.z, hi[4 * j + 2], lo[4 * j + 2]);
-            split_tf32(v.w, hi[4 * j + 3], lo[4 * j + 3]);
+            if (rna) {
+              split_act<true>(v.x, hi[4 * j + 0], lo[4 * j + 0]); split_act<true>(v.y, hi[4 * j + 1], lo[4 * j + 1]);
+              split_act<true>(v.z, hi[4 * j + 2], lo[4 * j + 2]); split_act<true>(v.w, hi[4 * j + 3], lo[4 * j + 3]);
+            } else {
+              split_act<false>(v.x, hi[4 * j + 0], lo[4 * j + 0]); split_act<false>(v.y, hi[4 * j + 1], lo[4 * j + 1]);
+              split_act<false>(v.z, hi[4 * j + 2], lo[4 * j + 2]); split_act<false>(v.w, hi[4 * j + 3], lo[4 * j + 3]);
+            }
           }
         } else {
           // G tile: four unswizzled [32 rows x 32 floats] boxes; this thread reads column r: a free transpose
@@ -394,7 +413,8 @@ tc3_gemm_kernel(const __grid_constant__ Maps maps, const Params P) {
             float v = lds32(col + m * 128);
             if (m >= valid) v = 0.f;                    // rows past the chunk / the row count may hold anything
             colsum += v;
-            split_tf32(v, hi[m], lo[m]);
+            if (rna) split_act<true>(v, hi[m], lo[m]);
+            else split_act<false>(v, hi[m], lo[m]);
           }
         }
         tmem_st32(trow + stage * A_STAGE_COLS, hi);
@@ -440,10 +460,17 @@ tc3_gemm_kernel(const __grid_constant__ Maps maps, const Params P) {
               float4 v = lds128(xb + c * 16);
               if (m >= valid) v = make_float4(0.f, 0.f, 0.f, 0.f);      // rows past the chunk / the row count
               uint32_t h[4], l[4];
-              split_tf32(v.x, h[0], l[0]); split_tf32(v.y, h[1], l[1]);
-              split_tf32(v.z, h[2], l[2]); split_tf32(v.w, h[3], l[3]);
-              sts128(xb + c * 16, make_float4(__uint_as_float(h[0]), __uint_as_float(h[1]), __uint_as_float(h[2]),
-                                              __uint_as_float(h[3])));
+              if (P.diag & DG_RNA_SPLIT) {
+                split_act<true>(v.x, h[0], l[0]); split_act<true>(v.y, h[1], l[1]);
+                split_act<true>(v.z, h[2], l[2]); split_act<true>(v.w, h[3], l[3]);
+              } else {
+                split_act<false>(v.x, h[0], l[0]); split_act<false>(v.y, h[1], l[1]);
+                split_act<false>(v.z, h[2], l[2]); split_act<false>(v.w, h[3], l[3]);
+              }
+              // truncation split: the raw tile already IS the hi operand (the tensor core ignores the 13 low bits)
+              if ((P.diag & DG_RNA_SPLIT) || m >= valid)
+                sts128(xb + c * 16, make_float4(__uint_as_float(h[0]), __uint_as_float(h[1]), __uint_as_float(h[2]),
+                                                __uint_as_float(h[3])));
               sts128(xb + TILE_BYTES + c * 16, make_float4(__uint_as_float(l[0]), __uint_as_float(l[1]),
                                                            __uint_as_float(l[2]), __uint_as_float(l[3])));
             }

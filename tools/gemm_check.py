@@ -24,14 +24,14 @@ def planes(W):
 
 
 def nt(X, Whl, b, Y, M, N, K, act, gen, m_dev=None, base_dev=None):
-    lib.gib_tc_debug(1 if gen == 1 else 0)
+    lib.gib_tc_debug({1: 1, 2: 0, 3: 512 << 8}[gen])      # 3 = second generation with the round-to-nearest split
     check(lib.gib_linear_fwd_tc_planes(P(X), X.shape[1], P(Whl[0]), P(Whl[1]), K, P(b), P(Y), Y.shape[1], M, N, K, act,
                                        P(m_dev), P(base_dev), st()), f"linear gen{gen}")
     lib.gib_tc_debug(0)
 
 
 def dw(G, X, M, N, K, gen, m_dev=None, base_dev=None, sc=None):
-    lib.gib_tc_debug(1 if gen == 1 else 0)
+    lib.gib_tc_debug({1: 1, 2: 0, 3: 512 << 8}[gen])
     dW = torch.zeros(N, K, device="cuda"); db = torch.zeros(N, device="cuda")
     if sc is None:
         sc = torch.empty(lib.gib_dw_scratch_bytes(M, N, K), dtype=torch.uint8, device="cuda")
@@ -98,7 +98,7 @@ for (M, N, K) in shapes:
     Whl = planes(W)
     ref = torch.nn.functional.linear(X.double(), W.double(), b.double())
     line = f"NT M={M:6d} N={N:4d} K={K:4d}:"
-    for gen in (2, 1):
+    for gen in (2, 3, 1):
         for act in (0, 1):
             r = torch.selu(ref) if act else ref
             Y = torch.full((M, N), float("nan"), device="cuda")
@@ -149,7 +149,7 @@ for (M, N, K) in shapes:
     G = torch.randn(M, N, device="cuda"); X = torch.randn(M, K, device="cuda")
     ref = G.double().t() @ X.double(); refb = G.double().sum(0)
     line = f"TN M={M:6d} N={N:4d} K={K:4d}:"
-    for gen in (2, 1):
+    for gen in (2, 3, 1):
         try:
             dW, db, sc = dw(G, X, M, N, K, gen)
             torch.cuda.synchronize()

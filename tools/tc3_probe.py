@@ -15,7 +15,7 @@ st = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 VARIANTS = [(0, "product"), (1, "no global stores"), (2, "no epilogue after the drain"), (2 | 64, "no drain, no epilogue"),
             (4, "no split / STTM"), (8, "no W_lo tile and MMAs"), (16, "no MMAs"), (32, "no TMA loads"),
             (4 | 16 | 2 | 64, "TMA only"), (32 | 4 | 2 | 64, "MMA only"), (32 | 4 | 2 | 64 | 256, "MMA only, interleaved"),
-            (256, "MMAs interleaved")]
+            (256, "MMAs interleaved"), (512, "round-to-nearest activation split")]
 shapes = [tuple(int(v) for v in a.split("x")) for a in sys.argv[1:]] or [(155648, 256, 256), (23808, 256, 256),
                                                                          (23808, 256, 128), (13312, 512, 512)]
 
@@ -71,7 +71,8 @@ for (M, N, K) in shapes:
     print(f"   {'first generation':34s} {t * 1e3:8.1f} us  {fl / t / 1e9:7.1f} TF/s", flush=True)
     lib.gib_tc_debug(0)
     print(f"== TN (weight gradient + reduction) {M}x{N}x{K}", flush=True)
-    for mask, name in [(0, "product"), (4, "no split / STTM"), (16, "no MMAs"), (32, "no TMA loads"), (2 | 64, "no drain, no epilogue")]:
+    for mask, name in [(0, "product"), (4, "no split / STTM"), (16, "no MMAs"), (32, "no TMA loads"), (2 | 64, "no drain, no epilogue"),
+                       (512, "round-to-nearest activation split")]:
         lib.gib_tc_debug(mask << 8)
         try:
             t = graph_time(lambda: check(lib.gib_linear_bwd_dw(P(G), N, N, P(X), K, K, M, P(dW), P(db), N, K, P(sc), None,
