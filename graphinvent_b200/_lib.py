@@ -39,6 +39,7 @@ _PROTOS = {
     "gib_tc_debug": (None, [c_i]),
     "gib_device_sm_count": (c_i, []),
     "gib_scatter_variant": (None, [c_i]),
+    "gib_tc_trace": (None, [c_p, c_i]),
     "gib_graph_count_ws_bytes": (c_sz, [c_p]),
     "gib_graph_count": (c_i, [c_p, c_p, c_p, c_p]),
     "gib_graph_header_capacity": (c_i, [c_p, c_i, c_p, c_p]),

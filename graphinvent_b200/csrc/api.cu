@@ -147,6 +147,7 @@ int gib_get_tensor_cores(void) { return g_use_tc ? 1 : 0; }
 void gib_tc_debug(int mode) { g_tc_debug = mode; }
 int gib_device_sm_count(void) { return device_sm_count(); }
 void gib_scatter_variant(int v) { g_scatter_variant = v; }
+void gib_tc_trace(long long* device_buf, int tiles) { tc3_set_trace(device_buf, tiles); }
 
 static int groups_of(const gib_dims* d) { return d->model == GIB_EMN ? 1 : d->Ef; }
 static bool is_cap(const int* hdr) { return hdr[HDR_CAPACITY] != 0; }

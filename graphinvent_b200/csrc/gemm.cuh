@@ -92,6 +92,7 @@ void tc3_dw_layout(const GemmDW* qs, int n, long long plan_rows, Dw3Layout* L);
 int gemm_dw_tc3_partials(const GemmDW* qs, int n, const Dw3Layout& L, float* scratch, cudaStream_t st);
 int gemm_dw_tc3_reduce(const GemmDW* qs, int n, const Dw3Layout& L, const float* scratch, cudaStream_t st);
 int device_sm_count();     // SMs of the current device (cached per device)
+void tc3_set_trace(long long* buf, int tiles);   // diagnosis: per-tile clock64 stamps of CTA 0
 // 2-D fp32 TMA descriptor (CUtensorMap*) with a [box_rows x 32 floats] box; 128-byte swizzle for K-major operand
 // tiles, its 32-byte-atom variant for MN-major ones (weight-gradient mode)
 int tc_make_map(void* cu_tensor_map, const float* base, int rows, int cols, int ld, int box_rows, int mn_major);

@@ -88,6 +88,8 @@ struct Params {
   int* flags;
   int nprob;
   int chunk_rows;           // TN: reduction rows per work item (multiple of 32)
+  long long* trace;         // diagnosis: per-tile clock64 stamps of CTA 0 ([tile][16] int64, gib_tc_trace), else nullptr
+  int trace_tiles;
   int diag;                 // timing experiments (gib_tc_debug >> 8; results are wrong with most of them):
                             //   1 no global stores   2 no epilogue after the drain   4 no split / STTM   8 no W_lo tile + MMAs
                             //   16 no MMAs   32 no TMA loads   64 no accumulator drain   128 rotate the k-block order per CTA
@@ -327,9 +329,20 @@ tc3_gemm_kernel(const __grid_constant__ Maps maps, const Params P) {
         const int nkb = decode_item<TN>(P, S, item).nkb;
         mbar_wait(acc_empty, (uint32_t)(it & 1) ^ 1);  // the epilogue holds the previous tile in registers
         tc_fence_after();
+        const bool tr = P.trace && blockIdx.x == 0 && it < P.trace_tiles;
+        long long w_full = 0, w_afull = 0;
+        if (tr) P.trace[it * 16 + 0] = clock64();
         for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(&full[stage], phase);              // W (TN: X) tiles landed (async proxy)
-          mbar_wait(&a_full[stage], phase);            // A pair is in TMEM (TN: X pair is split in smem)
+          if (tr) {
+            const long long t0 = clock64();
+            mbar_wait(&full[stage], phase);
+            const long long t1 = clock64();
+            mbar_wait(&a_full[stage], phase);
+            w_full += t1 - t0; w_afull += clock64() - t1;
+          } else {
+            mbar_wait(&full[stage], phase);              // W (TN: X) tiles landed (async proxy)
+            mbar_wait(&a_full[stage], phase);            // A pair is in TMEM (TN: X pair is split in smem)
+          }
           tc_fence_after();
           const uint32_t sb = smem_u32(smem + stage * STAGE_BYTES);
           const uint32_t a_hi = tmem_base + A_BASE + stage * A_STAGE_COLS, a_lo = a_hi + 32;
@@ -366,6 +379,7 @@ tc3_gemm_kernel(const __grid_constant__ Maps maps, const Params P) {
           if (kb == nkb - 1) umma_commit(acc_full);    // accumulators complete
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        if (tr) { P.trace[it * 16 + 1] = clock64(); P.trace[it * 16 + 2] = w_full; P.trace[it * 16 + 3] = w_afull; }
       }
     }
   } else if (warp < 2 + SPL_WARPS) {
@@ -380,8 +394,18 @@ tc3_gemm_kernel(const __grid_constant__ Maps maps, const Params P) {
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       const Item w = decode_item<TN>(P, S, item);
       float colsum = 0.f;
+      const int itn = (item - (int)blockIdx.x) / (int)gridDim.x;
+      const bool tr = P.trace && blockIdx.x == 0 && itn < P.trace_tiles && warp == 2 && lane == 0;
+      long long s_wait = 0, s_t0 = 0;
+      if (tr) s_t0 = clock64();
       for (int kb = 0; kb < w.nkb; ++kb) {
-        mbar_wait(&full[stage], phase);
+        if (tr) {
+          const long long t0 = clock64();
+          mbar_wait(&full[stage], phase);
+          s_wait += clock64() - t0;
+        } else {
+          mbar_wait(&full[stage], phase);
+        }
         tc_fence_after();
         if (P.diag & DG_NO_SPLIT) {
           mbar_arrive(&a_full[stage]);
@@ -428,6 +452,7 @@ tc3_gemm_kernel(const __grid_constant__ Maps maps, const Params P) {
         float* bp = P.bias_part[w.p];
         if (bp && w.n0 == 0 && w.m0 + r < P.tn_nn[w.p]) bp[(size_t)w.z * P.tn_nn[w.p] + w.m0 + r] = colsum;
       }
+      if (tr) { P.trace[itn * 16 + 8] = s_wait; P.trace[itn * 16 + 9] = clock64() - s_t0 - s_wait; }
     }
   } else {
     // ================= epilogue: TMEM -> registers (frees the accumulators) -> smem transpose -> global ============
@@ -490,6 +515,8 @@ tc3_gemm_kernel(const __grid_constant__ Maps maps, const Params P) {
       const int ncol0 = w.n0 + half * 64 + c4 * 4;                   // first of this lane's 4 column groups (stride 16)
       mbar_wait(acc_full, (uint32_t)(it & 1));
       tc_fence_after();
+      const bool tr = P.trace && blockIdx.x == 0 && it < P.trace_tiles && ew == 0 && lane == 0;
+      if (tr) P.trace[it * 16 + 4] = clock64();
       if constexpr (EPI != EPI_SPEC_GENERIC) {
         float acc[64];
         if (P.diag & DG_NO_DRAIN) {
@@ -508,6 +535,7 @@ tc3_gemm_kernel(const __grid_constant__ Maps maps, const Params P) {
         }
         tc_fence_before();
         mbar_arrive(acc_empty);                  // the MMA warp may overwrite the accumulators now
+        if (tr) P.trace[it * 16 + 5] = clock64();
         const float* const bias = g.bias;
 #pragma unroll
         for (int chunk = 0; chunk < 4; ++chunk) {
@@ -621,6 +649,7 @@ tc3_gemm_kernel(const __grid_constant__ Maps maps, const Params P) {
       }
       if constexpr (!TN)
         if (P.flags) signal_tile(P.flags + P.flag_off[w.p] + w.m0 / BM);
+      if (tr) P.trace[it * 16 + 6] = clock64();
     }
   }
 
@@ -761,6 +790,9 @@ static int make_map(CUtensorMap* map, const float* base, int rows, int cols, int
   return 0;
 }
 
+long long* g_trace = nullptr;   // gib_tc_trace
+int g_trace_tiles = 0;
+
 struct DevInfo { int num_sms = 0; bool attr_done = false; };
 static std::mutex g_dev_mu;
 static DevInfo g_dev[64];
@@ -801,6 +833,8 @@ static int epi_spec(const GemmNT& p) {
 }
 
 }  // namespace tc3
+
+void tc3_set_trace(long long* buf, int tiles) { tc3::g_trace = buf; tc3::g_trace_tiles = tiles; }
 
 int device_sm_count() {
   int n = 0;
@@ -862,6 +896,7 @@ static int launch_nt(const GemmNT* ps, const int* dep, int n, int* flags, cudaSt
   if (np == 0) return 0;
   P.nprob = np;
   P.diag = g_tc_debug >> 8;
+  P.trace = g_trace; P.trace_tiles = g_trace_tiles;
   if (dep) {
     P.flags = flags;
     GIB_CUDA_TRY(cudaMemsetAsync(flags, 0, (size_t)flag_ints * sizeof(int), st));
@@ -962,6 +997,7 @@ int gemm_dw_tc3_partials(const GemmDW* qs, int n, const Dw3Layout& L, float* scr
   P.nprob = n;
   P.chunk_rows = L.chunk_rows;
   P.diag = g_tc_debug >> 8;
+  P.trace = g_trace; P.trace_tiles = g_trace_tiles;
   const int grid = (int)(items < num_sms ? items : num_sms);
   tc3_gemm_kernel<true, EPI_SPEC_LINEAR><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps, P);
   GIB_LAUNCH_CHECK();

@@ -91,6 +91,11 @@ void gib_tc_debug(int mode);
 /* K2 scatter-aggregate variant (A/B measurements): bit 0 = two slots per thread, bit 1 = streaming cache hints;
  * default 2 (the fastest at the C4 shape).  Results are identical across variants. */
 void gib_scatter_variant(int v);
+/* diagnosis: while device_buf != NULL, CTA 0 of every second-generation GEMM launch writes clock64 stamps of its first
+ * `tiles` work items into device_buf[tile][16] (int64): 0 MMA start, 1 MMA last issue, 2 / 3 MMA cycles waiting for the
+ * TMA tiles / the split operand, 4 epilogue sees the accumulator, 5 accumulator drained, 6 tile stored, 8 / 9 splitter
+ * cycles waiting / working (tools/tc3_trace.py) */
+void gib_tc_trace(long long* device_buf, int tiles);
 /* streaming multiprocessors of the current device (grid sizing of the persistent kernels) */
 int gib_device_sm_count(void);
 
