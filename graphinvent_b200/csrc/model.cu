@@ -844,14 +844,22 @@ static int emn_forward(const Run& r, float* out) {
   const Lin& hh = pl.lins[pl.gru_hh];
   GIB_TRY(emn_input(r.ws + L.xin, L.embnn.ld[0], r.nodes, r.edges, d.in_dtype, r.ga.ent_dst, r.ga.ent_src, d.N, d.F,
                     d.Ef, E, r.st));
-  GIB_TRY(mlp_forward(r, pl.embnn, r.ws + L.xin, L.embnn, 0, E));
+  {   // the layers of an MLP run as one dependent-chain launch (mlp_forward_multi)
+    MlpJob j[1] = {{&pl.embnn, r.ws + L.xin, &L.embnn, 0, E, nullptr, 0, 0}};
+    GIB_TRY(mlp_forward_multi(r, j, 1, fwd_flags(r)));
+  }
   GIB_TRY(tanh_fwd(r.ws + L.xt, r.ws + L.embnn.y[pl.embnn.n], (long long)E * Hp, r.st));      // mpnn.py:469
-  GIB_TRY(mlp_forward(r, pl.emsg, r.ws + L.xt, L.emx, 0, E));
-  GIB_TRY(mlp_forward(r, pl.eatt, r.ws + L.xt, L.enx, 0, E));
+  {   // emb_msg_nn and att_msg_nn read the same rows: sibling chains in one launch
+    MlpJob j[2] = {{&pl.emsg, r.ws + L.xt, &L.emx, 0, E, nullptr, 0, 0}, {&pl.eatt, r.ws + L.xt, &L.enx, 0, E, nullptr, 0, 0}};
+    GIB_TRY(mlp_forward_multi(r, j, 2, fwd_flags(r)));
+  }
   if (E > 0) GIB_CUDA_TRY(cudaMemsetAsync(r.ws + L.mem[0], 0, (size_t)E * Hp * sizeof(float), r.st));
   for (int t = 0; t < d.T; ++t) {
-    GIB_TRY(mlp_forward(r, pl.emsg, r.ws + L.mem[t], L.emm[t], 0, E));
-    GIB_TRY(mlp_forward(r, pl.eatt, r.ws + L.mem[t], L.enm[t], 0, E));
+    {
+      MlpJob j[2] = {{&pl.emsg, r.ws + L.mem[t], &L.emm[t], 0, E, nullptr, 0, 0},
+                     {&pl.eatt, r.ws + L.mem[t], &L.enm[t], 0, E, nullptr, 0, 0}};
+      GIB_TRY(mlp_forward_multi(r, j, 2, fwd_flags(r)));
+    }
     GIB_TRY(emn_aggregate_fwd(r.ws + L.emsg[t], r.ws + L.emx.y[pl.emsg.n], r.ws + L.enx.y[pl.eatt.n],
                               r.ws + L.emm[t].y[pl.emsg.n], r.ws + L.enm[t].y[pl.eatt.n], Hp, r.ga.ent_dst,
                               r.ga.ent_src, r.ga.dst_ptr, E, r.st));
@@ -883,6 +891,7 @@ static int emn_backward(const Run& r, const BwdBufs& bb, const float* out, const
   float* dmem = sc + bb.dmem;      // d mem[t+1]
   float* dmem2 = sc + bb.dmem2;
   float* T1 = sc + bb.T1;
+  float* T2 = sc + bb.T2;
   GIB_TRY(gather_rows(dmem, sc + bb.dh, Hp, r.ga.ent_dst, nullptr, 0, E, r.st));
   GIB_CUDA_TRY(cudaMemsetAsync(sc + bb.dEMx, 0, EH * sizeof(float), r.st));
   GIB_CUDA_TRY(cudaMemsetAsync(sc + bb.dENx, 0, EH * sizeof(float), r.st));
@@ -905,17 +914,26 @@ static int emn_backward(const Run& r, const BwdBufs& bb, const float* out, const
     GIB_TRY(emn_aggregate_bwd(sc + bb.dEMx, sc + bb.dENx, sc + bb.dEMm, sc + bb.dENm, sc + bb.st3, sc + bb.dmsum,
                               r.ws + L.emx.y[pl.emsg.n], r.ws + L.enx.y[pl.eatt.n], EMm, ENm, Hp, r.ga, E, r.st));
     GIB_TRY(mul_dselu(T1, sc + bb.dEMm, EMm, EH, r.st));
-    GIB_TRY(mlp_backward(r, bb, pl.emsg, r.ws + L.mem[t], L.emm[t], 0, E, T1, dmem2, Hp, nullptr));
-    GIB_TRY(mul_dselu(T1, sc + bb.dENm, ENm, EH, r.st));
-    GIB_TRY(mlp_backward(r, bb, pl.eatt, r.ws + L.mem[t], L.enm[t], 0, E, T1, dmem, Hp, dmem2));
+    GIB_TRY(mul_dselu(T2, sc + bb.dENm, ENm, EH, r.st));
+    {   // sibling MLPs on the same rows: chained input gradients + one grouped weight-gradient launch
+      MlpBwdJob j[2] = {{&pl.emsg, r.ws + L.mem[t], &L.emm[t], 0, E, T1, dmem2, Hp, nullptr},
+                        {&pl.eatt, r.ws + L.mem[t], &L.enm[t], 0, E, T2, dmem, Hp, dmem2}};
+      GIB_TRY(mlp_backward_multi(r, bb, j, 2));
+    }
   }
   // pass-independent branch through x = tanh(embedding_nn(.))
   GIB_TRY(mul_dselu(T1, sc + bb.dEMx, r.ws + L.emx.y[pl.emsg.n], EH, r.st));
-  GIB_TRY(mlp_backward(r, bb, pl.emsg, r.ws + L.xt, L.emx, 0, E, T1, dmem2, Hp, nullptr));
-  GIB_TRY(mul_dselu(T1, sc + bb.dENx, r.ws + L.enx.y[pl.eatt.n], EH, r.st));
-  GIB_TRY(mlp_backward(r, bb, pl.eatt, r.ws + L.xt, L.enx, 0, E, T1, dmem, Hp, dmem2));
+  GIB_TRY(mul_dselu(T2, sc + bb.dENx, r.ws + L.enx.y[pl.eatt.n], EH, r.st));
+  {
+    MlpBwdJob j[2] = {{&pl.emsg, r.ws + L.xt, &L.emx, 0, E, T1, dmem2, Hp, nullptr},
+                      {&pl.eatt, r.ws + L.xt, &L.enx, 0, E, T2, dmem, Hp, dmem2}};
+    GIB_TRY(mlp_backward_multi(r, bb, j, 2));
+  }
   GIB_TRY(tanh_selu_bwd(T1, dmem, r.ws + L.xt, r.ws + L.embnn.y[pl.embnn.n], EH, r.st));
-  GIB_TRY(mlp_backward(r, bb, pl.embnn, r.ws + L.xin, L.embnn, 0, E, T1, nullptr, 0, nullptr));
+  {
+    MlpBwdJob j[1] = {{&pl.embnn, r.ws + L.xin, &L.embnn, 0, E, T1, nullptr, 0, nullptr}};
+    GIB_TRY(mlp_backward_multi(r, bb, j, 1));
+  }
   return 0;
 }
 
@@ -975,6 +993,11 @@ void make_bwd(const Run& r, BwdBufs& bb) {
     mlp_extent(pl, pl.embnn, E, big, dw);
     mlp_extent(pl, pl.emsg, E, big, dw);
     mlp_extent(pl, pl.eatt, E, big, dw);
+    const Mlp* one[1] = {&pl.embnn}; const size_t re[2] = {E, E};
+    group_extent(pl, one, re, 1, 0, dw);
+    const Mlp* two[2] = {&pl.emsg, &pl.eatt};
+    group_extent(pl, two, re, 2, 0, dw);
+    big = std::max(big, E * (mlp_max_ld(pl, pl.emsg) + mlp_max_ld(pl, pl.eatt)) + 64);
   }
   const size_t gru_rows = d.model == GIB_EMN ? E : S;
   dw = std::max(dw, gemm_dw_scratch_floats((int)gru_rows, pl.lins[pl.gru_ih].Rp, pl.lins[pl.gru_ih].Cp));
