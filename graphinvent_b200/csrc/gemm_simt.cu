@@ -209,7 +209,7 @@ int gemm_nt_group(const GemmNT* ps, int n, cudaStream_t st) {
 // Dependent chain (the layers of sibling MLPs): ONE persistent tensor-core launch when every member qualifies,
 // else layer by layer through gemm_nt_group (members of one layer = consecutive problems with equal `layer`).
 bool gemm_nt_chain_ok(const GemmNT* ps, int n) {
-  if (!g_use_tc || !use_tc3() || n < 2 || n > kTc3MaxProblems) return false;
+  if (!g_use_tc || !use_tc3() || n < 2 || n > kTc3MaxProblems || (g_tc_debug & 2)) return false;
   long long tiles = 0;
   bool dyn = false;
   for (int i = 0; i < n; ++i) {
