@@ -88,7 +88,8 @@ int gemm_nt_tc3_group(const GemmNT* ps, int n, cudaStream_t st);
 size_t tc3_chain_flag_ints(const GemmNT* ps, int n);
 int gemm_nt_tc3_chain(const GemmNT* ps, const int* dep, int n, int* flags, cudaStream_t st);
 bool tc3_dw_eligible(const GemmDW& q);
-void tc3_dw_layout(const GemmDW* qs, int n, long long plan_rows, Dw3Layout* L);
+int tc3_dw_chunk_rows(const GemmDW* qs, int n, long long plan_rows);   // from ALL members of a group (sizing == run time)
+void tc3_dw_layout(const GemmDW* qs, int n, int chunk_rows, Dw3Layout* L);
 int gemm_dw_tc3_partials(const GemmDW* qs, int n, const Dw3Layout& L, float* scratch, cudaStream_t st);
 int gemm_dw_tc3_reduce(const GemmDW* qs, int n, const Dw3Layout& L, const float* scratch, cudaStream_t st);
 int device_sm_count();     // SMs of the current device (cached per device)

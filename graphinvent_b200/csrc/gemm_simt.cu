@@ -533,7 +533,7 @@ size_t gemm_dw_half_floats(int M, int Nn, int Kk) {
   size_t f = (((size_t)splits * Nn * Kk + (size_t)(splits > kColsumSplits ? splits : kColsumSplits) * Nn) + 63) & ~(size_t)63;
   GemmDW q; q.M = M; q.Nn = Nn; q.Kk = Kk;
   Dw3Layout L;
-  tc3_dw_layout(&q, 1, 0, &L);
+  tc3_dw_layout(&q, 1, tc3_dw_chunk_rows(&q, 1, 0), &L);
   return std::max(f, (L.floats + 63) & ~(size_t)63);
 }
 
@@ -546,7 +546,7 @@ size_t gemm_dw_group_half_floats(const GemmDW* qs, int n, long long plan_rows) {
   size_t f = 0;
   for (int i = 0; i < n; ++i) f = std::max(f, gemm_dw_half_floats(qs[i].M, qs[i].Nn, qs[i].Kk));
   Dw3Layout L;
-  tc3_dw_layout(qs, n, plan_rows, &L);
+  tc3_dw_layout(qs, n, tc3_dw_chunk_rows(qs, n, plan_rows), &L);
   return std::max(f, (L.floats + 63) & ~(size_t)63);
 }
 
@@ -607,8 +607,8 @@ int gemm_dw_group(const GemmDW* qs, int n, long long plan_rows, cudaStream_t st)
   GIB_TRY(dw_side(&d));
   const int half = (int)(d->calls++ & 1);
   float* const scratch = live[0].scratch + (size_t)half * live[0].half_floats;
-  Dw3Layout L;
-  tc3_dw_layout(live, nl, plan_rows, &L);
+  Dw3Layout L;       // chunk from ALL members (as the scratch was sized), offsets for the grouped ones
+  tc3_dw_layout(live, nl, tc3_dw_chunk_rows(qs, n, plan_rows), &L);
   if (L.floats > live[0].half_floats) {
     set_error("gemm_dw_group: scratch half of %zu floats is too small for %zu", live[0].half_floats, L.floats);
     return -2;

@@ -51,7 +51,8 @@ constexpr int TILE_BYTES = BM * BKF * 4;          // 16 KB
 constexpr int STAGE_BYTES = 3 * TILE_BYTES;       // NT: A raw | W hi | W lo      TN: G raw | X raw -> hi | X lo
 constexpr int SPL_WARPS = 4, EPI_WARPS = 8;
 constexpr int NUM_THREADS = 64 + 32 * SPL_WARPS + 32 * EPI_WARPS;   // 448
-constexpr int EPI_STG_BYTES = 32 * 16 * 4;        // per-warp 32 x 16 staging tile, 64 B rows, XOR-swizzled 16 B chunks
+constexpr int EPI_STG_BYTES = 32 * 32 * 4;        // per-warp 32 x 32 staging tile, 128 B rows, XOR-swizzled 16 B chunks
+                                                  // (the generic epilogue uses it as 32 x 16)
 constexpr int OFF_BARS = STAGES * STAGE_BYTES;
 constexpr int OFF_SCHED = OFF_BARS + 256;
 constexpr int OFF_STG = OFF_SCHED + 512;
@@ -59,6 +60,7 @@ constexpr int SMEM_BYTES = OFF_STG + EPI_WARPS * EPI_STG_BYTES + 1024 /*align sl
 constexpr int TMEM_COLS = 512;
 constexpr uint32_t ACC_MAIN = 0, ACC_X = 128, A_BASE = 256, A_STAGE_COLS = 64;
 
+constexpr int kMaxChunkRows = 4096;   // <= 512 truncating accumulations per TMEM accumulator and work item
 constexpr int MAXP = kTc3MaxProblems;   // 16: e.g. the 5 layers x 3 bond types of a message MLP as one dependent chain
 
 // instruction descriptor, kind::tf32: D = F32 (bits 4-5 = 1), A/B = TF32 (bits 7-9, 10-12 = 2), N >> 3 at bits 17-22,
@@ -225,11 +227,11 @@ tc3_gemm_kernel(const __grid_constant__ Maps maps, const Params P) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&a_full[s], TN ? 32 * (SPL_WARPS + EPI_WARPS) : 32 * SPL_WARPS);
+      mbar_init(&a_full[s], TN ? SPL_WARPS + EPI_WARPS : SPL_WARPS);   // one arrival per warp (after __syncwarp)
       mbar_init(&empty[s], 1);
     }
     mbar_init(acc_full, 1);
-    mbar_init(acc_empty, 32 * EPI_WARPS);
+    mbar_init(acc_empty, EPI_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     int total = 0;
     for (int p = 0; p < P.nprob; ++p) {
@@ -408,7 +410,8 @@ tc3_gemm_kernel(const __grid_constant__ Maps maps, const Params P) {
         }
         tc_fence_after();
         if (P.diag & DG_NO_SPLIT) {
-          mbar_arrive(&a_full[stage]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&a_full[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
           continue;
         }
@@ -445,7 +448,8 @@ tc3_gemm_kernel(const __grid_constant__ Maps maps, const Params P) {
         tmem_st32(trow + stage * A_STAGE_COLS + 32, lo);
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(&a_full[stage]);
+        __syncwarp();                          // every lane's tcgen05.st has completed and is fenced:
+        if (lane == 0) mbar_arrive(&a_full[stage]);   // one arrival per warp (128 arrivals per k-block serialise on the barrier)
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
       if constexpr (TN) {
@@ -501,7 +505,8 @@ tc3_gemm_kernel(const __grid_constant__ Maps maps, const Params P) {
             }
             fence_proxy_async();       // generic-proxy smem writes -> visible to the tensor-core (async) proxy
           }
-          mbar_arrive(&a_full[stage]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&a_full[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -534,32 +539,38 @@ tc3_gemm_kernel(const __grid_constant__ Maps maps, const Params P) {
           }
         }
         tc_fence_before();
-        mbar_arrive(acc_empty);                  // the MMA warp may overwrite the accumulators now
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty);   // the MMA warp may overwrite the accumulators now
         if (tr) P.trace[it * 16 + 5] = clock64();
         const float* const bias = g.bias;
+        // 32-column chunks: a staging row is one 128-byte line, so every 128-bit store instruction of the warp writes
+        // 4 rows x 128 contiguous bytes = 4 full lines (16-column chunks wrote 8 half lines per instruction)
+        const int rr8 = lane >> 3, c8 = lane & 7;
+        const uint32_t st_wr32 = stg + lane * 128;
+        const uint32_t swz32 = (uint32_t)lane & 7u;
 #pragma unroll
-        for (int chunk = 0; chunk < 4; ++chunk) {
+        for (int chunk = 0; chunk < 2; ++chunk) {
           if (P.diag & DG_NO_EPI) break;
           __syncwarp();
-          // lane = tile row; 16-byte chunk j of row `lane` is stored at chunk (j ^ ((lane >> 1) & 3)): 8 consecutive
-          // rows hit 8 distinct bank groups on the write, and the 2 rows x 4 chunks of a read phase do as well
+          // lane = tile row; 16-byte chunk j of row `lane` sits at chunk (j ^ (lane & 7)) -- the 128B-swizzle pattern:
+          // the 8 rows of a write phase and the 8 chunks of a read phase both cover all 32 banks exactly once
 #pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4)
-            sts128(st_wr + (((uint32_t)j4 ^ swz_wr) << 4),
-                   make_float4(acc[chunk * 16 + j4 * 4 + 0], acc[chunk * 16 + j4 * 4 + 1],
-                               acc[chunk * 16 + j4 * 4 + 2], acc[chunk * 16 + j4 * 4 + 3]));
+          for (int j8 = 0; j8 < 8; ++j8)
+            sts128(st_wr32 + (((uint32_t)j8 ^ swz32) << 4),
+                   make_float4(acc[chunk * 32 + j8 * 4 + 0], acc[chunk * 32 + j8 * 4 + 1],
+                               acc[chunk * 32 + j8 * 4 + 2], acc[chunk * 32 + j8 * 4 + 3]));
           __syncwarp();
-          const int n = ncol0 + chunk * 16;
+          const int n = w.n0 + half * 64 + chunk * 32 + c8 * 4;
           if (n < n_store) {
             float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if constexpr (EPI == EPI_SPEC_SELU || EPI == EPI_SPEC_LINEAR)
               if (bias) b4 = __ldg(reinterpret_cast<const float4*>(bias + n));
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int row = i * 8 + rr;
-              const int m = mrow0 + i * 8;
+            for (int i = 0; i < 8; ++i) {
+              const int row = i * 4 + rr8;
+              const int m = w.m0 + q * 32 + row;
               if (m < Mrows) {
-                float4 v = lds128(stg + row * 64 + (((uint32_t)c4 ^ (((uint32_t)row >> 1) & 3u)) << 4));
+                float4 v = lds128(stg + row * 128 + (((uint32_t)c8 ^ ((uint32_t)row & 7u)) << 4));
                 if constexpr (EPI == EPI_SPEC_SELU) {
                   v.x = act_fast(v.x + b4.x, ACT_SELU); v.y = act_fast(v.y + b4.y, ACT_SELU);
                   v.z = act_fast(v.z + b4.z, ACT_SELU); v.w = act_fast(v.w + b4.w, ACT_SELU);
@@ -645,7 +656,8 @@ tc3_gemm_kernel(const __grid_constant__ Maps maps, const Params P) {
           }
         }
         tc_fence_before();
-        mbar_arrive(acc_empty);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty);
       }
       if constexpr (!TN)
         if (P.flags) signal_tile(P.flags + P.flag_off[w.p] + w.m0 / BM);
@@ -934,14 +946,14 @@ bool tc3_dw_eligible(const GemmDW& q) {
          (q.ldx % 4) == 0 && al(q.G) && al(q.X);
 }
 
-// Scratch layout of a group: per problem [cap_splits][Nn][Kk] partial products, then [cap_splits][Nn] bias partials.
-// chunk_rows is chosen so that the group gives about one work item per SM.
-void tc3_dw_layout(const GemmDW* qs, int n, long long plan_rows, Dw3Layout* L) {
+// Reduction rows per work item for a group: about one work item per SM, within [256, kMaxChunkRows].
+int tc3_dw_chunk_rows(const GemmDW* qs, int n, long long plan_rows) {
   using namespace tc3;
   const int num_sms = device_sm_count();
   int max_tiles = 1;
   long long rows = 0;
   for (int i = 0; i < n; ++i) {
+    if (qs[i].M <= 0) continue;
     max_tiles = std::max(max_tiles, ceil_div(qs[i].Nn, BM) * ceil_div(qs[i].Kk, BN));
     rows += qs[i].M;
   }
@@ -949,9 +961,14 @@ void tc3_dw_layout(const GemmDW* qs, int n, long long plan_rows, Dw3Layout* L) {
   long long c = ceil_div_ll(rows * max_tiles, num_sms);
   c = ceil_div_ll(c, BKF) * BKF;
   if (c < 8 * BKF) c = 8 * BKF;                       // >= 256 reduction rows per item: amortise the 64 KB tile drain
-  if (c > 32 * BKF) c = 32 * BKF;                     // <= 1024: the tensor core accumulates with truncation, keep the
-                                                      // chains in one accumulator short (more items than SMs is fine)
-  L->chunk_rows = (int)c;
+  if (c > kMaxChunkRows) c = kMaxChunkRows;           // the tensor core accumulates with truncation: bounded chains
+  return (int)c;
+}
+
+// Scratch layout of a group: per problem [cap_splits][Nn][Kk] partial products, then [cap_splits][Nn] bias partials.
+void tc3_dw_layout(const GemmDW* qs, int n, int chunk_rows, Dw3Layout* L) {
+  using namespace tc3;
+  L->chunk_rows = chunk_rows;
   size_t off = 0;
   for (int i = 0; i < MAXP; ++i) {
     if (i < n) {

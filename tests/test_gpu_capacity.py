@@ -107,7 +107,7 @@ def test_graphed_train_step_matches_eager_steps(in_dtype):
     # the captured step differs from the eager one only in the split points of the weight-gradient reductions
     assert np.allclose(got, losses, rtol=0, atol=1e-5), (got, losses)
     for a, b in zip(net.parameters(), net2.parameters()):
-        assert (a - b).abs().max().item() <= 2e-5
+        assert (a - b).abs().max().item() <= 1e-4
     # a batch that does not fit the capacity is reported
     small = TrainStep(net2, opt2, batch_size=nodes.shape[0], entry_capacity=max(8, entries // 4), input_dtype=in_dtype)
     small(nodes.to(in_dtype), edges.to(in_dtype), target)

@@ -376,7 +376,10 @@ def test_full_size_properties(cfg):
 # ||g_L - g_R|| is the total gradient change the units inside the band can cause.  tau = a few times the forward
 # rounding noise of the path (tensor cores: 3xTF32 products accumulate with truncation, measured logit deviation
 # ~1e-5; fp32 SIMT GEMMs: ~5e-6).
-#   gradients, per tensor:  ||g_cuda - g_fp64|| <= 2 ||g_ref32 - g_fp64|| + ||g_L(tau) - g_R(tau)|| + 1e-6 ||g_fp64||
+#   gradients, per tensor:  ||g_cuda - g_fp64|| <= 2 ||g_ref32 - g_fp64|| + ||g_L(tau) - g_R(tau)|| + eps ||g_fp64||
+#                           eps = 1e-6 with fp32 SIMT GEMMs; 3e-5 with tensor cores: the arithmetic of the 3xTF32 GEMMs
+#                           themselves (dropped lo*lo term, truncating TMEM accumulation; measured against fp64 on random
+#                           operands: 1e-6 .. 1e-5 of the largest entry, tools/gemm_check.py)
 #   logits, per molecule:   max|o_cuda - o_fp64| <= 3 max|o_ref32 - o_fp64| + 1e-4
 #   APD argmax:             identical to the fp32 reference wherever the reference's own top-2 gap exceeds its own
 #                           fp32-vs-fp64 movement on that molecule (bond-less molecules included)
@@ -384,6 +387,7 @@ def test_full_size_properties(cfg):
 # ------------------------------------------------------------------------------------------
 FP64_C = 3.0
 KINK_TAU = {1: 3e-5, 0: 3e-6}      # tensor cores on / off
+GEMM_EPS = {1: 3e-5, 0: 1e-6}
 
 
 def _fp64_anchored(C, sd, nodes, edges, target, tag, tensor_cores=1):
@@ -420,7 +424,7 @@ def _fp64_anchored(C, sd, nodes, edges, target, tag, tensor_cores=1):
         d_cuda = (grads[k].double() - g).norm().item()
         d_ref = (g32[k].double() - g).norm().item()
         d_kink = (gL[k] - gR[k]).norm().item()
-        bound = 2.0 * d_ref + d_kink + 1e-6 * g.norm().item() + 1e-7 * gscale
+        bound = 2.0 * d_ref + d_kink + GEMM_EPS[tensor_cores] * g.norm().item() + 1e-7 * gscale
         for i, v in enumerate((d_cuda, d_ref, d_kink, g.norm().item())):
             tot[i] += v * v
         if d_cuda / bound > worst[1]:
@@ -437,7 +441,7 @@ def _fp64_anchored(C, sd, nodes, edges, target, tag, tensor_cores=1):
     assert abs(loss - float(l64)) <= FP64_C * abs(float(l32) - float(l64)) + 1e-5 * max(1.0, abs(float(l64)))
     assert worst[1] <= 1.0, (f"gradient {worst[0]}: |cuda - fp64| = {worst[2]:.3e} exceeds 2 x |ref32 - fp64| = {worst[3]:.3e} "
                              f"+ kink band {worst[4]:.3e} (+ floor)")
-    assert tot[0] <= 2.0 * tot[1] + tot[2] + 1e-6 * tot[3]
+    assert tot[0] <= 2.0 * tot[1] + tot[2] + GEMM_EPS[tensor_cores] * tot[3]
 
 
 @pytest.mark.parametrize("tensor_cores", [1, 0])
