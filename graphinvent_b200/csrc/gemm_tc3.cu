@@ -565,12 +565,18 @@ tc3_gemm_kernel(const __grid_constant__ Maps maps, const Params P) {
             float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if constexpr (EPI == EPI_SPEC_SELU || EPI == EPI_SPEC_LINEAR)
               if (bias) b4 = __ldg(reinterpret_cast<const float4*>(bias + n));
+            float4 vv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {      // all 8 staging reads in flight before any arithmetic
+              const int row = i * 4 + rr8;
+              vv[i] = lds128(stg + row * 128 + (((uint32_t)c8 ^ ((uint32_t)row & 7u)) << 4));
+            }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int row = i * 4 + rr8;
               const int m = w.m0 + q * 32 + row;
               if (m < Mrows) {
-                float4 v = lds128(stg + row * 128 + (((uint32_t)c8 ^ ((uint32_t)row & 7u)) << 4));
+                float4 v = vv[i];
                 if constexpr (EPI == EPI_SPEC_SELU) {
                   v.x = act_fast(v.x + b4.x, ACT_SELU); v.y = act_fast(v.y + b4.y, ACT_SELU);
                   v.z = act_fast(v.z + b4.z, ACT_SELU); v.w = act_fast(v.w + b4.w, ACT_SELU);
