@@ -96,10 +96,11 @@ struct Params {
                             //   1 no global stores   2 no epilogue after the drain   4 no split / STTM   8 no W_lo tile + MMAs
                             //   16 no MMAs   32 no TMA loads   64 no accumulator drain   128 rotate the k-block order per CTA
                             //   256 interleave the MMAs of the two accumulators   512 round-to-nearest activation split
+                            //   1024 TN: no proxy fence after the X split (timing only)
                             //   (results stay correct with 128, 256, 512)
 };
 enum { DG_NO_STORE = 1, DG_NO_EPI = 2, DG_NO_SPLIT = 4, DG_NO_BLO = 8, DG_NO_MMA = 16, DG_NO_TMA = 32, DG_NO_DRAIN = 64,
-       DG_ROTATE = 128, DG_INTERLEAVE = 256, DG_RNA_SPLIT = 512 };
+       DG_ROTATE = 128, DG_INTERLEAVE = 256, DG_RNA_SPLIT = 512, DG_NO_PFENCE = 1024 };
 
 struct Sched {              // computed once per CTA from host values or the device-side row counts
   int M[MAXP], base[MAXP], begin[MAXP + 1], splits[MAXP];
@@ -503,7 +504,8 @@ tc3_gemm_kernel(const __grid_constant__ Maps maps, const Params P) {
               sts128(xb + TILE_BYTES + c * 16, make_float4(__uint_as_float(l[0]), __uint_as_float(l[1]),
                                                            __uint_as_float(l[2]), __uint_as_float(l[3])));
             }
-            fence_proxy_async();       // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+            if (!(P.diag & DG_NO_PFENCE))
+              fence_proxy_async();     // generic-proxy smem writes -> visible to the tensor-core (async) proxy
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(&a_full[stage]);

@@ -72,7 +72,7 @@ for (M, N, K) in shapes:
     lib.gib_tc_debug(0)
     print(f"== TN (weight gradient + reduction) {M}x{N}x{K}", flush=True)
     for mask, name in [(0, "product"), (4, "no split / STTM"), (16, "no MMAs"), (32, "no TMA loads"), (2 | 64, "no drain, no epilogue"),
-                       (512, "round-to-nearest activation split")]:
+                       (512, "round-to-nearest activation split"), (1024, "no proxy fence after the X split")]:
         lib.gib_tc_debug(mask << 8)
         try:
             t = graph_time(lambda: check(lib.gib_linear_bwd_dw(P(G), N, N, P(X), K, K, M, P(dW), P(db), N, K, P(sc), None,
