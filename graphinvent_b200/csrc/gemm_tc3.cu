@@ -97,10 +97,13 @@ struct Params {
                             //   16 no MMAs   32 no TMA loads   64 no accumulator drain   128 rotate the k-block order per CTA
                             //   256 interleave the MMAs of the two accumulators   512 round-to-nearest activation split
                             //   1024 TN: no proxy fence after the X split (timing only)
+                            //   2048 three accumulators / 4096 N = 256 MMAs (timing only, with the MMA-only switches)
+                            //   8192 epilogue without the smem transpose / 16384 without the activation math (timing only)
                             //   (results stay correct with 128, 256, 512)
 };
 enum { DG_NO_STORE = 1, DG_NO_EPI = 2, DG_NO_SPLIT = 4, DG_NO_BLO = 8, DG_NO_MMA = 16, DG_NO_TMA = 32, DG_NO_DRAIN = 64,
-       DG_ROTATE = 128, DG_INTERLEAVE = 256, DG_RNA_SPLIT = 512, DG_NO_PFENCE = 1024 };
+       DG_ROTATE = 128, DG_INTERLEAVE = 256, DG_RNA_SPLIT = 512, DG_NO_PFENCE = 1024, DG_ACC3 = 2048, DG_N256 = 4096,
+       DG_NO_STAGE = 8192, DG_NO_MATH = 16384 };
 
 struct Sched {              // computed once per CTA from host values or the device-side row counts
   int M[MAXP], base[MAXP], begin[MAXP + 1], splits[MAXP];
@@ -361,7 +364,21 @@ tc3_gemm_kernel(const __grid_constant__ Maps maps, const Params P) {
             idesc = IDESC_TN;
           }
           // grouped by accumulator so that consecutive MMAs chain on the same TMEM tile
-          if (P.diag & DG_INTERLEAVE) {          // experiment: alternate the two accumulators k-step by k-step
+          if (P.diag & DG_ACC3) {                // experiment (garbage operands): one accumulator per product type
+#pragma unroll
+            for (int k = 0; k < BKF / 8; ++k) {
+              umma_tf32_ts(tmem_base + 0, tmem_base + 384 + 8 * k, d_bhi + k * kstep, idesc, (kb | k) != 0);
+              umma_tf32_ts(tmem_base + 128, tmem_base + 416 + 8 * k, d_bhi + k * kstep, idesc, (kb | k) != 0);
+              umma_tf32_ts(tmem_base + 256, tmem_base + 384 + 8 * k, d_blo + k * kstep, idesc, (kb | k) != 0);
+            }
+          } else if (P.diag & DG_N256) {         // experiment (garbage operands): the same FLOPs as 6 N = 256 MMAs
+            const uint32_t idesc256 = (idesc & ~(0x3fu << 17)) | ((uint32_t)(256 >> 3) << 17);
+#pragma unroll
+            for (int k = 0; k < BKF / 8; ++k) {
+              umma_tf32_ts(tmem_base + 0, a_hi + 8 * k, d_bhi + k * kstep, idesc256, (kb | k) != 0);
+              if (k & 1) umma_tf32_ts(tmem_base + 0, a_lo + 8 * k, d_bhi + k * kstep, idesc256, 1);
+            }
+          } else if (P.diag & DG_INTERLEAVE) {   // experiment: alternate the two accumulators k-step by k-step
 #pragma unroll
             for (int k = 0; k < BKF / 8; ++k) {
               umma_tf32_ts(tmem_d, a_hi + 8 * k, d_bhi + k * kstep, idesc, (kb | k) != 0);
@@ -558,7 +575,7 @@ tc3_gemm_kernel(const __grid_constant__ Maps maps, const Params P) {
           // the 8 rows of a write phase and the 8 chunks of a read phase both cover all 32 banks exactly once
 #pragma unroll
           for (int j8 = 0; j8 < 8; ++j8)
-            sts128(st_wr32 + (((uint32_t)j8 ^ swz32) << 4),
+            if (!(P.diag & DG_NO_STAGE)) sts128(st_wr32 + (((uint32_t)j8 ^ swz32) << 4),
                    make_float4(acc[chunk * 32 + j8 * 4 + 0], acc[chunk * 32 + j8 * 4 + 1],
                                acc[chunk * 32 + j8 * 4 + 2], acc[chunk * 32 + j8 * 4 + 3]));
           __syncwarp();
@@ -571,7 +588,9 @@ tc3_gemm_kernel(const __grid_constant__ Maps maps, const Params P) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {      // all 8 staging reads in flight before any arithmetic
               const int row = i * 4 + rr8;
-              vv[i] = lds128(stg + row * 128 + (((uint32_t)c8 ^ ((uint32_t)row & 7u)) << 4));
+              if (P.diag & DG_NO_STAGE) vv[i] = make_float4(acc[chunk * 32 + 4 * i], acc[chunk * 32 + 4 * i + 1],
+                                                            acc[chunk * 32 + 4 * i + 2], acc[chunk * 32 + 4 * i + 3]);
+              else vv[i] = lds128(stg + row * 128 + (((uint32_t)c8 ^ ((uint32_t)row & 7u)) << 4));
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -579,7 +598,8 @@ tc3_gemm_kernel(const __grid_constant__ Maps maps, const Params P) {
               const int m = w.m0 + q * 32 + row;
               if (m < Mrows) {
                 float4 v = vv[i];
-                if constexpr (EPI == EPI_SPEC_SELU) {
+                if (P.diag & DG_NO_MATH) {
+                } else if constexpr (EPI == EPI_SPEC_SELU) {
                   v.x = act_fast(v.x + b4.x, ACT_SELU); v.y = act_fast(v.y + b4.y, ACT_SELU);
                   v.z = act_fast(v.z + b4.z, ACT_SELU); v.w = act_fast(v.w + b4.w, ACT_SELU);
                 } else if constexpr (EPI == EPI_SPEC_LINEAR) {
@@ -966,10 +986,16 @@ int tc3_dw_chunk_rows(const GemmDW* qs, int n, long long plan_rows) {
     rows += qs[i].M;
   }
   if (plan_rows > 0) rows = plan_rows;
-  long long c = ceil_div_ll(rows * max_tiles, num_sms);
-  c = ceil_div_ll(c, BKF) * BKF;
+  // whole rounds of work items: r rounds of num_sms items, the fewest rounds whose chunk respects the cap (a capped
+  // chunk that leaves a few items for an extra round would double the kernel time)
+  long long c = 8 * BKF;
+  for (int r = 1; r <= 64; ++r) {
+    c = ceil_div_ll(rows * max_tiles, (long long)r * num_sms);
+    c = ceil_div_ll(c, BKF) * BKF;
+    if (c <= kMaxChunkRows) break;                    // the tensor core accumulates with truncation: bounded chains
+  }
+  if (c > kMaxChunkRows) c = kMaxChunkRows;
   if (c < 8 * BKF) c = 8 * BKF;                       // >= 256 reduction rows per item: amortise the 64 KB tile drain
-  if (c > kMaxChunkRows) c = kMaxChunkRows;           // the tensor core accumulates with truncation: bounded chains
   return (int)c;
 }
 

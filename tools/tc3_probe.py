@@ -15,7 +15,10 @@ st = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 VARIANTS = [(0, "product"), (1, "no global stores"), (2, "no epilogue after the drain"), (2 | 64, "no drain, no epilogue"),
             (4, "no split / STTM"), (8, "no W_lo tile and MMAs"), (16, "no MMAs"), (32, "no TMA loads"),
             (4 | 16 | 2 | 64, "TMA only"), (32 | 4 | 2 | 64, "MMA only"), (32 | 4 | 2 | 64 | 256, "MMA only, interleaved"),
-            (256, "MMAs interleaved"), (512, "round-to-nearest activation split")]
+            (256, "MMAs interleaved"), (512, "round-to-nearest activation split"),
+            (32 | 4 | 2 | 64 | 2048, "MMA only, three accumulators"), (32 | 4 | 2 | 64 | 4096, "MMA only, N = 256 instructions"),
+            (8192, "epilogue without the smem transpose"), (16384, "epilogue without the activation math"),
+            (8192 | 16384, "epilogue: drain + stores only")]
 shapes = [tuple(int(v) for v in a.split("x")) for a in sys.argv[1:]] or [(155648, 256, 256), (23808, 256, 256),
                                                                          (23808, 256, 128), (13312, 512, 512)]
 
