@@ -99,11 +99,12 @@ struct Params {
                             //   1024 TN: no proxy fence after the X split (timing only)
                             //   2048 three accumulators / 4096 N = 256 MMAs (timing only, with the MMA-only switches)
                             //   8192 epilogue without the smem transpose / 16384 without the activation math (timing only)
+                            //   32768 twelve N = 128 MMAs per k-block instead of 4 x (N = 256 + N = 128) (correct)
                             //   (results stay correct with 128, 256, 512)
 };
 enum { DG_NO_STORE = 1, DG_NO_EPI = 2, DG_NO_SPLIT = 4, DG_NO_BLO = 8, DG_NO_MMA = 16, DG_NO_TMA = 32, DG_NO_DRAIN = 64,
        DG_ROTATE = 128, DG_INTERLEAVE = 256, DG_RNA_SPLIT = 512, DG_NO_PFENCE = 1024, DG_ACC3 = 2048, DG_N256 = 4096,
-       DG_NO_STAGE = 8192, DG_NO_MATH = 16384 };
+       DG_NO_STAGE = 8192, DG_NO_MATH = 16384, DG_MMA12 = 32768 };
 
 struct Sched {              // computed once per CTA from host values or the device-side row counts
   int M[MAXP], base[MAXP], begin[MAXP + 1], splits[MAXP];
@@ -384,6 +385,17 @@ tc3_gemm_kernel(const __grid_constant__ Maps maps, const Params P) {
               umma_tf32_ts(tmem_d, a_hi + 8 * k, d_bhi + k * kstep, idesc, (kb | k) != 0);
               umma_tf32_ts(tmem_x, a_lo + 8 * k, d_bhi + k * kstep, idesc, (kb | k) != 0);
               umma_tf32_ts(tmem_x, a_hi + 8 * k, d_blo + k * kstep, idesc, 1);
+            }
+          } else if (!(P.diag & (DG_NO_MMA | DG_MMA12))) {
+            // 8 instead of 12 instructions per k-block: the W_hi and W_lo tiles are adjacent in the stage, so ONE N = 256
+            // MMA computes a_hi * [W_hi | W_lo]: hi*hi into the main accumulator (columns 0-127) and hi*lo into the
+            // cross-term accumulator (columns 128-255); a_lo * W_hi follows as an N = 128 MMA.  A tf32 MMA carries a
+            // fixed cost of ~40 cycles per instruction (measured: N = 128: 108 cycles, N = 256: 182).
+            const uint32_t idesc256 = (idesc & ~(0x3fu << 17)) | ((uint32_t)(256 >> 3) << 17);
+#pragma unroll
+            for (int k = 0; k < BKF / 8; ++k) {
+              umma_tf32_ts(tmem_d, a_hi + 8 * k, d_bhi + k * kstep, idesc256, (kb | k) != 0);
+              umma_tf32_ts(tmem_x, a_lo + 8 * k, d_bhi + k * kstep, idesc, 1);
             }
           } else if (!(P.diag & DG_NO_MMA)) {
 #pragma unroll

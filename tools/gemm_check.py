@@ -24,14 +24,14 @@ def planes(W):
 
 
 def nt(X, Whl, b, Y, M, N, K, act, gen, m_dev=None, base_dev=None):
-    lib.gib_tc_debug({1: 1, 2: 0, 3: 512 << 8}[gen])      # 3 = second generation with the round-to-nearest split
+    lib.gib_tc_debug({1: 1, 2: 0, 3: 32768 << 8}[gen])      # 3 = second generation with twelve N = 128 MMAs per k-block
     check(lib.gib_linear_fwd_tc_planes(P(X), X.shape[1], P(Whl[0]), P(Whl[1]), K, P(b), P(Y), Y.shape[1], M, N, K, act,
                                        P(m_dev), P(base_dev), st()), f"linear gen{gen}")
     lib.gib_tc_debug(0)
 
 
 def dw(G, X, M, N, K, gen, m_dev=None, base_dev=None, sc=None):
-    lib.gib_tc_debug({1: 1, 2: 0, 3: 512 << 8}[gen])
+    lib.gib_tc_debug({1: 1, 2: 0, 3: 32768 << 8}[gen])
     dW = torch.zeros(N, K, device="cuda"); db = torch.zeros(N, device="cuda")
     if sc is None:
         sc = torch.empty(lib.gib_dw_scratch_bytes(M, N, K), dtype=torch.uint8, device="cuda")
