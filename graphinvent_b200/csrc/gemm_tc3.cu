@@ -99,12 +99,13 @@ struct Params {
                             //   1024 TN: no proxy fence after the X split (timing only)
                             //   2048 three accumulators / 4096 N = 256 MMAs (timing only, with the MMA-only switches)
                             //   8192 epilogue without the smem transpose / 16384 without the activation math (timing only)
+                            //   65536 splitters without the software pipeline (correct)
                             //   32768 twelve N = 128 MMAs per k-block instead of 4 x (N = 256 + N = 128) (correct)
                             //   (results stay correct with 128, 256, 512)
 };
 enum { DG_NO_STORE = 1, DG_NO_EPI = 2, DG_NO_SPLIT = 4, DG_NO_BLO = 8, DG_NO_MMA = 16, DG_NO_TMA = 32, DG_NO_DRAIN = 64,
        DG_ROTATE = 128, DG_INTERLEAVE = 256, DG_RNA_SPLIT = 512, DG_NO_PFENCE = 1024, DG_ACC3 = 2048, DG_N256 = 4096,
-       DG_NO_STAGE = 8192, DG_NO_MATH = 16384, DG_MMA12 = 32768 };
+       DG_NO_STAGE = 8192, DG_NO_MATH = 16384, DG_MMA12 = 32768, DG_NO_SPLIT_PIPE = 65536 };
 
 struct Sched {              // computed once per CTA from host values or the device-side row counts
   int M[MAXP], base[MAXP], begin[MAXP + 1], splits[MAXP];
@@ -430,52 +431,64 @@ tc3_gemm_kernel(const __grid_constant__ Maps maps, const Params P) {
       const bool tr = P.trace && blockIdx.x == 0 && itn < P.trace_tiles && warp == 2 && lane == 0;
       long long s_wait = 0, s_t0 = 0;
       if (tr) s_t0 = clock64();
-      for (int kb = 0; kb < w.nkb; ++kb) {
+      // software pipeline: the raw operand of k-block kb + 1 is loaded (barrier wait + shared-memory latency) while the
+      // two tcgen05.st of k-block kb are in flight; the warp handles its k-blocks strictly one after the other, so its
+      // per-k-block LATENCY (not its instruction count) is what must stay below the MMA time of a k-block.
+      float v[32];
+      auto load_raw = [&](int stg_i, uint32_t ph, int kb) {
         if (tr) {
           const long long t0 = clock64();
-          mbar_wait(&full[stage], phase);
+          mbar_wait(&full[stg_i], ph);
           s_wait += clock64() - t0;
         } else {
-          mbar_wait(&full[stage], phase);
+          mbar_wait(&full[stg_i], ph);
         }
         tc_fence_after();
-        if (P.diag & DG_NO_SPLIT) {
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&a_full[stage]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-          continue;
-        }
-        const uint32_t sb = smem_u32(smem + stage * STAGE_BYTES);
-        uint32_t hi[32], lo[32];
+        if (P.diag & DG_NO_SPLIT) return;
+        const uint32_t sb = smem_u32(smem + stg_i * STAGE_BYTES);
         if constexpr (!TN) {
           // row r of the 128B-swizzled tile: logical 16-byte chunk j sits at chunk (j ^ (r & 7))
           const uint32_t rowaddr = sb + r * 128;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 v = lds128(rowaddr + (((uint32_t)j ^ ((uint32_t)r & 7u)) << 4));
-            if (rna) {
-              split_act<true>(v.x, hi[4 * j + 0], lo[4 * j + 0]); split_act<true>(v.y, hi[4 * j + 1], lo[4 * j + 1]);
-              split_act<true>(v.z, hi[4 * j + 2], lo[4 * j + 2]); split_act<true>(v.w, hi[4 * j + 3], lo[4 * j + 3]);
-            } else {
-              split_act<false>(v.x, hi[4 * j + 0], lo[4 * j + 0]); split_act<false>(v.y, hi[4 * j + 1], lo[4 * j + 1]);
-              split_act<false>(v.z, hi[4 * j + 2], lo[4 * j + 2]); split_act<false>(v.w, hi[4 * j + 3], lo[4 * j + 3]);
-            }
+            const float4 q4 = lds128(rowaddr + (((uint32_t)j ^ ((uint32_t)r & 7u)) << 4));
+            v[4 * j + 0] = q4.x; v[4 * j + 1] = q4.y; v[4 * j + 2] = q4.z; v[4 * j + 3] = q4.w;
           }
         } else {
           // G tile: four unswizzled [32 rows x 32 floats] boxes; this thread reads column r: a free transpose
           const int valid = w.rows - kb * BKF;          // reduction rows of this k-block that exist (>= 1)
           const uint32_t col = sb + (uint32_t)(r >> 5) * 4096 + (uint32_t)(r & 31) * 4;
 #pragma unroll
-          for (int m = 0; m < 32; ++m) {
-            float v = lds32(col + m * 128);
-            if (m >= valid) v = 0.f;                    // rows past the chunk / the row count may hold anything
-            colsum += v;
-            if (rna) split_act<true>(v, hi[m], lo[m]);
-            else split_act<false>(v, hi[m], lo[m]);
+          for (int m = 0; m < 32; ++m) v[m] = lds32(col + m * 128);
+          if (valid < 32) {                             // rows past the chunk / the row count may hold anything
+#pragma unroll
+            for (int m = 0; m < 32; ++m)
+              if (m >= valid) v[m] = 0.f;
           }
+        }
+      };
+      const bool pipe = !(P.diag & DG_NO_SPLIT_PIPE);
+      if (pipe && w.nkb > 0) load_raw(stage, phase, 0);
+      for (int kb = 0; kb < w.nkb; ++kb) {
+        if (!pipe) load_raw(stage, phase, kb);
+        if (P.diag & DG_NO_SPLIT) {
+          if (pipe && kb + 1 < w.nkb) load_raw(stage + 1 == STAGES ? 0 : stage + 1, stage + 1 == STAGES ? phase ^ 1 : phase, kb + 1);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&a_full[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          continue;
+        }
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int m = 0; m < 32; ++m) {
+          if constexpr (TN) colsum += v[m];
+          if (rna) split_act<true>(v[m], hi[m], lo[m]);
+          else split_act<false>(v[m], hi[m], lo[m]);
         }
         tmem_st32(trow + stage * A_STAGE_COLS, hi);
         tmem_st32(trow + stage * A_STAGE_COLS + 32, lo);
+        if (pipe && kb + 1 < w.nkb)
+          load_raw(stage + 1 == STAGES ? 0 : stage + 1, stage + 1 == STAGES ? phase ^ 1 : phase, kb + 1);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();                          // every lane's tcgen05.st has completed and is fenced:
@@ -507,8 +520,17 @@ tc3_gemm_kernel(const __grid_constant__ Maps maps, const Params P) {
         // the epilogue warps idle during a work item's k-loop: they split the X tile (MN-major B operand) of every
         // k-block -- raw -> hi in place, lo into the sibling tile at the same (swizzled) offset
         const int et = threadIdx.x - 32 * (2 + SPL_WARPS);           // 0..255
+        const bool trx = P.trace && blockIdx.x == 0 && it < P.trace_tiles && ew == 0 && lane == 0;
+        long long x_wait = 0;
+        const long long x_t0 = trx ? clock64() : 0;
         for (int kb = 0; kb < w.nkb; ++kb) {
-          mbar_wait(&full[stage], phase);
+          if (trx) {
+            const long long t0 = clock64();
+            mbar_wait(&full[stage], phase);
+            x_wait += clock64() - t0;
+          } else {
+            mbar_wait(&full[stage], phase);
+          }
           if (!(P.diag & DG_NO_SPLIT)) {
             const int valid = w.rows - kb * BKF;
             const uint32_t xb = smem_u32(smem + stage * STAGE_BYTES) + TILE_BYTES;
@@ -540,6 +562,7 @@ tc3_gemm_kernel(const __grid_constant__ Maps maps, const Params P) {
           if (lane == 0) mbar_arrive(&a_full[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        if (trx) { P.trace[it * 16 + 10] = x_wait; P.trace[it * 16 + 11] = clock64() - x_t0 - x_wait; }
       }
       const GemmNT& g = P.g[w.p];
       const int Mrows = TN ? P.tn_nn[w.p] : S.M[w.p];

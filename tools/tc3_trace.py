@@ -1,6 +1,6 @@
 """GPU: per-tile timeline of CTA 0 of the second-generation GEMM (gib_tc_trace): when does the MMA warp start / finish a
 tile, how long does it wait for TMA tiles / the split operand, when does the epilogue see, drain and store the tile.
-    python tools/tc3_trace.py [MxNxK] [tiles]"""
+    python tools/tc3_trace.py [MxNxK] [tiles] [tn]      (tn: the weight-gradient kernel, one line per work item)"""
 import ctypes
 import sys
 
@@ -35,3 +35,30 @@ for mask, name in [(0, "product"), (1, "no global stores"), (2, "no epilogue aft
         r = t[i]
         print(f"{i:4d} {int(r[0]) - t0:10d} {int(r[1]) - t0:9d}  ({int(r[2]):6d}, {int(r[3]):6d})   {int(r[4]) - t0:9d} {int(r[5]) - t0:8d} {int(r[6]) - t0:8d}   | "
               f"{int(r[8]):6d} / {int(r[9]):6d}")
+
+if "tn" in sys.argv[1:]:
+    G = torch.randn(M, N, device="cuda")
+    sc = torch.empty(lib.gib_dw_scratch_bytes(M, N, K), dtype=torch.uint8, device="cuda")
+    dW = torch.zeros(N, K, device="cuda"); db = torch.zeros(N, device="cuda")
+    run = lambda: check(lib.gib_linear_bwd_dw(P(G), N, N, P(X), K, K, M, P(dW), P(db), N, K, P(sc), None, None, st()), "dw")
+    for mask, name in [(0, "product"), (65536, "splitters without the software pipeline"), (4, "no split")]:
+        buf = torch.zeros(tiles, 16, dtype=torch.int64, device="cuda")
+        lib.gib_tc_debug(mask << 8)
+        for _ in range(2):
+            run()
+        lib.gib_tc_trace(P(buf), tiles)
+        run()
+        torch.cuda.synchronize()
+        lib.gib_tc_trace(None, 0)
+        lib.gib_tc_debug(0)
+        t = buf.cpu()
+        t0 = int(t[0, 0])
+        print(f"== TN {name}: cycles relative to the first MMA start of CTA 0")
+        print("item  mma_start  mma_last  (wait tma, wait split)   epi_sees  drained   stored   | G splitter wait / work"
+              " | X splitter wait / work")
+        for i in range(tiles):
+            r = t[i]
+            if int(r[0]) == 0:
+                break
+            print(f"{i:4d} {int(r[0]) - t0:10d} {int(r[1]) - t0:9d}  ({int(r[2]):6d}, {int(r[3]):6d})   {int(r[4]) - t0:9d} "
+                  f"{int(r[5]) - t0:8d} {int(r[6]) - t0:8d}   | {int(r[8]):6d} / {int(r[9]):6d} | {int(r[10]):6d} / {int(r[11]):6d}")
