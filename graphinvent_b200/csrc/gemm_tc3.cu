@@ -419,7 +419,6 @@ tc3_gemm_kernel(const __grid_constant__ Maps maps, const Params P) {
     // ================= splitters: fp32 -> (hi, lo) TF32 pairs, registers -> TMEM =================
     const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
     const int r = quarter * 32 + lane;                  // tile row (NT) / G column (TN) this thread owns
-    const int t = threadIdx.x - 64;                     // 0..127 (TN: work split of the X tile)
     const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + A_BASE;
     const bool rna = (P.diag & DG_RNA_SPLIT) != 0;
     int stage = 0;
@@ -479,11 +478,16 @@ tc3_gemm_kernel(const __grid_constant__ Maps maps, const Params P) {
           continue;
         }
         uint32_t hi[32], lo[32];
+        if constexpr (TN) {
 #pragma unroll
-        for (int m = 0; m < 32; ++m) {
-          if constexpr (TN) colsum += v[m];
-          if (rna) split_act<true>(v[m], hi[m], lo[m]);
-          else split_act<false>(v[m], hi[m], lo[m]);
+          for (int m = 0; m < 32; ++m) colsum += v[m];
+        }
+        if (rna) {                             // one branch per k-block: per-element selects made ptxas run BOTH splits
+#pragma unroll
+          for (int m = 0; m < 32; ++m) split_act<true>(v[m], hi[m], lo[m]);
+        } else {
+#pragma unroll
+          for (int m = 0; m < 32; ++m) split_act<false>(v[m], hi[m], lo[m]);
         }
         tmem_st32(trow + stage * A_STAGE_COLS, hi);
         tmem_st32(trow + stage * A_STAGE_COLS + 32, lo);

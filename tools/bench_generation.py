@@ -44,12 +44,17 @@ def train_weights(model_name, steps, dev):
     apds = torch.from_numpy(z["apds"]).float().to(dev)
     opt = FlatAdam(net.parameters(), lr=3e-4)
     loss = None
-    for _ in range(steps):
+    keep = {0, 1, 2, 5, 10, 20, 39, 100, 200, steps - 1}
+    traj = {}
+    for i in range(steps):
         out = net(nodes, edges)
         loss = Fn.kl_loss(out, apds)
         opt.zero_grad(set_to_none=True)
         loss.backward()
         opt.step()
+        if i in keep:
+            traj[i] = loss.detach()
+    train_weights.trajectory = {str(k): round(float(v), 4) for k, v in traj.items()}
     return C, net.eval(), (float(loss.detach()) if loss is not None else None)
 
 
@@ -163,11 +168,14 @@ def main():
                             f"seeded recipe: {args.train_steps} Adam steps (lr 3e-4) on 256 real gdb13 rows, final loss {train_loss:.4f}, {t_train:.1f} s"),
                 "config": {"workload": "GraphGenerator.sample 100k-molecule batched generation, EMN model, 8xB200 embarrassingly parallel",
                            "name": "C5"}}
+        if getattr(train_weights, "trajectory", None):
+            line["train_loss_trajectory"] = train_weights.trajectory
         if not args.no_cpu:
             try:
                 line["cpu_reference"] = cpu_reference_generation(C, net.state_dict(), args.batch, args.model)
             except Exception as ex:
-                line["cpu_reference"] = {"error": repr(ex)}
+                import traceback
+                line["cpu_reference"] = {"error": repr(ex), "where": traceback.format_exc().splitlines()[-8:]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
