@@ -492,6 +492,20 @@ def run_b200_arm(args):
     pv1.record()
     barrier()
     ms_instr = max_over_ranks(pv0.elapsed_time(pv1))
+    if args.launch_table and rank == 0:
+        cap_ = 1 << 16
+        rms = (ctypes.c_double * cap_)(); rwork = (ctypes.c_double * cap_)(); rcls = (ctypes.c_int * cap_)()
+        nrec = lib.gib_profile_records(rms, rwork, rcls, cap_)
+        per = nrec // prof_steps if nrec > 0 and nrec % prof_steps == 0 and nrec <= cap_ else 0
+        with open(args.launch_table, "w") as fh:
+            fh.write(f"# {cfg}: timed launches of one eager forward + loss + backward (mean of {prof_steps} steps), "
+                     "launch order; class 0 = forward/dX GEMM launch (a chain = several layers), 1 = dW partials, 2 = K2\n")
+            fh.write("idx class  GFLOP_or_MB      us     TFLOP/s_or_GB/s\n")
+            for i in range(per):
+                t = sum(rms[i + k * per] for k in range(prof_steps)) / prof_steps
+                wk = rwork[i]
+                rate = wk / (t * 1e-3) / (1e12 if rcls[i] < 2 else 1e9) if t > 0 else 0.0
+                fh.write(f"{i:3d} {rcls[i]:5d} {wk / (1e9 if rcls[i] < 2 else 1e6):12.3f} {t * 1e3:8.1f} {rate:10.1f}\n")
     pms = (ctypes.c_double * 3)(); pwork = (ctypes.c_double * 3)(); pcnt = (ctypes.c_longlong * 3)()
     check(lib.gib_profile_collect(pms, pwork, pcnt), "profile_collect")
     lib.gib_profile_enable(0)
@@ -700,6 +714,7 @@ def main():
     ap.add_argument("--no-module-api", action="store_true")
     ap.add_argument("--no-single", action="store_true", help="N > 1: skip the single-GPU run of the same workload")
     ap.add_argument("--no-k2-in-model", action="store_true")
+    ap.add_argument("--launch-table", default=None, help="write the per-launch timing table of the eager pass here")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     if args.config is None:

@@ -76,6 +76,7 @@ _PROTOS = {
     "gib_profile_enable": (None, [c_i]),
     "gib_launch_count": (c_ll, []),
     "gib_profile_collect": (c_i, [c_p, c_p, c_p]),
+    "gib_profile_records": (c_i, [c_p, c_p, c_p, c_i]),
 }
 
 

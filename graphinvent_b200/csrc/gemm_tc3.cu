@@ -99,13 +99,13 @@ struct Params {
                             //   1024 TN: no proxy fence after the X split (timing only)
                             //   2048 three accumulators / 4096 N = 256 MMAs (timing only, with the MMA-only switches)
                             //   8192 epilogue without the smem transpose / 16384 without the activation math (timing only)
-                            //   65536 splitters without the software pipeline (correct)
+                            //   65536 splitters with a software pipeline: next operand loaded under the tcgen05.st (correct)
                             //   32768 twelve N = 128 MMAs per k-block instead of 4 x (N = 256 + N = 128) (correct)
                             //   (results stay correct with 128, 256, 512)
 };
 enum { DG_NO_STORE = 1, DG_NO_EPI = 2, DG_NO_SPLIT = 4, DG_NO_BLO = 8, DG_NO_MMA = 16, DG_NO_TMA = 32, DG_NO_DRAIN = 64,
        DG_ROTATE = 128, DG_INTERLEAVE = 256, DG_RNA_SPLIT = 512, DG_NO_PFENCE = 1024, DG_ACC3 = 2048, DG_N256 = 4096,
-       DG_NO_STAGE = 8192, DG_NO_MATH = 16384, DG_MMA12 = 32768, DG_NO_SPLIT_PIPE = 65536 };
+       DG_NO_STAGE = 8192, DG_NO_MATH = 16384, DG_MMA12 = 32768, DG_SPLIT_PIPE = 65536 };
 
 struct Sched {              // computed once per CTA from host values or the device-side row counts
   int M[MAXP], base[MAXP], begin[MAXP + 1], splits[MAXP];
@@ -430,9 +430,9 @@ tc3_gemm_kernel(const __grid_constant__ Maps maps, const Params P) {
       const bool tr = P.trace && blockIdx.x == 0 && itn < P.trace_tiles && warp == 2 && lane == 0;
       long long s_wait = 0, s_t0 = 0;
       if (tr) s_t0 = clock64();
-      // software pipeline: the raw operand of k-block kb + 1 is loaded (barrier wait + shared-memory latency) while the
-      // two tcgen05.st of k-block kb are in flight; the warp handles its k-blocks strictly one after the other, so its
-      // per-k-block LATENCY (not its instruction count) is what must stay below the MMA time of a k-block.
+      // optional software pipeline (diag 65536): the raw operand of k-block kb + 1 is loaded while the two tcgen05.st of
+      // k-block kb are in flight.  The warp handles its k-blocks strictly one after the other, so its per-k-block
+      // LATENCY must stay below the MMA time of a k-block; measured, the plain order already does.
       float v[32];
       auto load_raw = [&](int stg_i, uint32_t ph, int kb) {
         if (tr) {
@@ -466,7 +466,7 @@ tc3_gemm_kernel(const __grid_constant__ Maps maps, const Params P) {
           }
         }
       };
-      const bool pipe = !(P.diag & DG_NO_SPLIT_PIPE);
+      const bool pipe = (P.diag & DG_SPLIT_PIPE) != 0;   // measured: NT equal, TN 9 % slower with it (r02_tc3_probe_stage4.txt)
       if (pipe && w.nkb > 0) load_raw(stage, phase, 0);
       for (int kb = 0; kb < w.nkb; ++kb) {
         if (!pipe) load_raw(stage, phase, kb);
@@ -609,6 +609,19 @@ tc3_gemm_kernel(const __grid_constant__ Maps maps, const Params P) {
 #pragma unroll
         for (int chunk = 0; chunk < 2; ++chunk) {
           if (P.diag & DG_NO_EPI) break;
+          // the auxiliary operand (layer output / residual) of the 8 rows this lane finishes: all 8 loads are issued
+          // before the staging round trip -- inside the store loop each load sat behind the previous row's store
+          // (possible alias) and the warp paid a full global-memory latency per row
+          float4 xx[8];
+          if constexpr (EPI == EPI_SPEC_DSELU || EPI == EPI_SPEC_ADD) {
+            const int n = w.n0 + half * 64 + chunk * 32 + c8 * 4;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int m = w.m0 + q * 32 + i * 4 + rr8;
+              xx[i] = (n < n_store && m < Mrows) ? __ldg(reinterpret_cast<const float4*>(Xbase + (size_t)m * ldaux + n))
+                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
           __syncwarp();
           // lane = tile row; 16-byte chunk j of row `lane` sits at chunk (j ^ (lane & 7)) -- the 128B-swizzle pattern:
           // the 8 rows of a write phase and the 8 chunks of a read phase both cover all 32 banks exactly once
@@ -644,7 +657,7 @@ tc3_gemm_kernel(const __grid_constant__ Maps maps, const Params P) {
                 } else if constexpr (EPI == EPI_SPEC_LINEAR) {
                   v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
                 } else {
-                  const float4 x = __ldg(reinterpret_cast<const float4*>(Xbase + (size_t)m * ldaux + n));
+                  const float4 x = xx[i];
                   if constexpr (EPI == EPI_SPEC_DSELU) {
                     v.x *= dselu_from_out(x.x); v.y *= dselu_from_out(x.y);
                     v.z *= dselu_from_out(x.z); v.w *= dselu_from_out(x.w);

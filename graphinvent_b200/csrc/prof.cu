@@ -43,6 +43,18 @@ void gib_profile_enable(int on) {
   if (on) g_used = 0;
 }
 
+// Per-launch records since gib_profile_enable(1), in launch order (call before gib_profile_collect, which clears them):
+// fills at most cap entries and returns the number of records (or a negative CUDA error).
+int gib_profile_records(double* ms, double* work, int* cls, int cap) {
+  for (size_t i = 0; i < g_used && (int)i < cap; ++i) {
+    float t = 0.f;
+    cudaError_t e = cudaEventElapsedTime(&t, g_pool[i].a, g_pool[i].b);
+    if (e != cudaSuccess) return -(int)e;
+    ms[i] = t; work[i] = g_pool[i].work; cls[i] = g_pool[i].cls;
+  }
+  return (int)g_used;
+}
+
 // Call after synchronising the stream.  For each class c: ms[c] = summed event time,
 // work[c] = summed algorithmic FLOPs (GEMM classes) or bytes (scatter), count[c] = launches.
 int gib_profile_collect(double* ms, double* work, long long* count) {

@@ -129,8 +129,18 @@ __device__ __forceinline__ uint32_t to_tf32(float x) {
 
 // epilogue activation: SELU through the hardware exp2 path (MUFU), |abs err| <~ 2e-7 -- the four epilogue warps
 // must stay under the MMA time per tile, and expm1f's ~30-instruction software path does not
+// Branch-free: with `x > 0 ? a : b * (__expf(x) - 1)` ptxas emitted a divergent branch (BSSY / BRA / BSYNC) per
+// element -- 64 per thread and tile -- and the epilogue warps, not the tensor core, set the tile time
+// (profiles/r02_tc3_probe_stage4.txt).  ex2.approx.ftz of a large positive argument is +inf: not selected.
+__device__ __forceinline__ float selu_fast(float x) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 1.4426950408889634f));
+  const float neg = fmaf(e, GIB_SELU_SCALE * GIB_SELU_ALPHA, -(GIB_SELU_SCALE * GIB_SELU_ALPHA));
+  const float pos = GIB_SELU_SCALE * x;
+  return x > 0.f ? pos : neg;
+}
 __device__ __forceinline__ float act_fast(float x, int act) {
-  if (act == ACT_SELU) return x > 0.f ? GIB_SELU_SCALE * x : (GIB_SELU_SCALE * GIB_SELU_ALPHA) * (__expf(x) - 1.f);
+  if (act == ACT_SELU) return selu_fast(x);
   if (act == ACT_TANH) return tanhf(x);
   return x;
 }

@@ -226,6 +226,8 @@ int gib_generation_round(int B, int N, int F, int Ef, int n_atom_types, int n_ch
 void gib_profile_enable(int on);
 long long gib_launch_count(void); /* kernels launched by this library since load */
 int gib_profile_collect(double* ms, double* work, long long* count);
+/* per-launch records in launch order (before gib_profile_collect, which clears them): returns their number */
+int gib_profile_records(double* ms, double* work, int* cls, int cap);
 
 #ifdef __cplusplus
 }

@@ -13,7 +13,7 @@ from graphinvent_b200._lib import check, lib  # noqa: E402
 P = lambda t: ctypes.c_void_p(t.data_ptr() if t is not None else 0)
 st = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 VARIANTS = [(0, "product"), (32768, "twelve N=128 MMAs per k-block"),
-            (65536, "splitters without the software pipeline"), (1, "no global stores"), (2, "no epilogue after the drain"), (2 | 64, "no drain, no epilogue"),
+            (65536, "splitters with the software pipeline"), (1, "no global stores"), (2, "no epilogue after the drain"), (2 | 64, "no drain, no epilogue"),
             (4, "no split / STTM"), (8, "no W_lo tile and MMAs"), (16, "no MMAs"), (32, "no TMA loads"),
             (4 | 16 | 2 | 64, "TMA only"), (32 | 4 | 2 | 64, "MMA only"), (32 | 4 | 2 | 64 | 256, "MMA only, interleaved"),
             (256, "MMAs interleaved"), (512, "round-to-nearest activation split"),
@@ -76,7 +76,7 @@ for (M, N, K) in shapes:
     lib.gib_tc_debug(0)
     print(f"== TN (weight gradient + reduction) {M}x{N}x{K}", flush=True)
     for mask, name in [(0, "product"), (32768, "twelve N=128 MMAs per k-block"),
-                       (65536, "splitters without the software pipeline"), (4, "no split / STTM"), (16, "no MMAs"), (32, "no TMA loads"), (2 | 64, "no drain, no epilogue"),
+                       (65536, "splitters with the software pipeline"), (4, "no split / STTM"), (16, "no MMAs"), (32, "no TMA loads"), (2 | 64, "no drain, no epilogue"),
                        (512, "round-to-nearest activation split"), (1024, "no proxy fence after the X split")]:
         lib.gib_tc_debug(mask << 8)
         try:

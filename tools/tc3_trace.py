@@ -41,7 +41,7 @@ if "tn" in sys.argv[1:]:
     sc = torch.empty(lib.gib_dw_scratch_bytes(M, N, K), dtype=torch.uint8, device="cuda")
     dW = torch.zeros(N, K, device="cuda"); db = torch.zeros(N, device="cuda")
     run = lambda: check(lib.gib_linear_bwd_dw(P(G), N, N, P(X), K, K, M, P(dW), P(db), N, K, P(sc), None, None, st()), "dw")
-    for mask, name in [(0, "product"), (65536, "splitters without the software pipeline"), (4, "no split")]:
+    for mask, name in [(0, "product"), (65536, "splitters with the software pipeline"), (4, "no split")]:
         buf = torch.zeros(tiles, 16, dtype=torch.int64, device="cuda")
         lib.gib_tc_debug(mask << 8)
         for _ in range(2):
