@@ -451,9 +451,23 @@ static int mlp_forward_multi(const Run& r, const MlpJob* jobs, int n, int* flags
   }
   if (try_chain && nall) {
     if (flags && gemm_nt_chain_ok(all, nall)) return gemm_nt_chain(all, dep, nall, flags, r.st);
-    // not eligible as a chain (tiny / unaligned members, tensor cores off): layer by layer (members of a layer are
+    // a narrow output layer (the 3 / 39 / 45-wide APD heads) must not cost the hidden layers their chain: the longest
+    // prefix of whole layers that qualifies runs as a chain, the rest layer by layer (members of a layer are
     // contiguous in `all`)
-    for (int k0 = 0; k0 < nall;) {
+    int k0 = 0;
+    if (flags) {
+      int k = nall;
+      while (k > 0 && layer_of[k - 1] >= 3) {              // candidate prefixes: layers 1..l for l = depth-1 .. 2
+        const int l = layer_of[k - 1];
+        while (k > 0 && layer_of[k - 1] == l) --k;
+        if (gemm_nt_chain_ok(all, k)) {
+          GIB_TRY(gemm_nt_chain(all, dep, k, flags, r.st));
+          k0 = k;
+          break;
+        }
+      }
+    }
+    while (k0 < nall) {
       int k1 = k0 + 1;
       while (k1 < nall && layer_of[k1] == layer_of[k0]) ++k1;
       GIB_TRY(gemm_nt_group(all + k0, k1 - k0, r.st));
@@ -518,15 +532,20 @@ static int mlp_backward_multi(const Run& r, const BwdBufs& bb, const MlpBwdJob* 
       last[i] = nall++;
     }
   if (nall) {
-    if (nall >= 2 && gemm_nt_chain_ok(all, nall)) {
-      GIB_TRY(gemm_nt_chain(all, dep, nall, reinterpret_cast<int*>(r.scratch + bb.flags), r.st));
-    } else {
-      for (int k0 = 0; k0 < nall;) {
-        int k1 = k0 + 1;
-        while (k1 < nall && layer_of[k1] == layer_of[k0]) ++k1;
-        GIB_TRY(gemm_nt_group(all + k0, k1 - k0, r.st));
-        k0 = k1;
+    // the top layer of an APD head reduces over 3 / 39 / 45 columns and does not qualify for the tensor-core chain:
+    // leading layers run one by one until the remaining suffix of whole layers qualifies as a chain
+    int k0 = 0;
+    while (k0 < nall) {
+      if (nall - k0 >= 2 && gemm_nt_chain_ok(all + k0, nall - k0)) {
+        int dep2[kTc3MaxProblems];
+        for (int k = k0; k < nall; ++k) dep2[k - k0] = dep[k] >= k0 ? dep[k] - k0 : -1;   // earlier layers: stream order
+        GIB_TRY(gemm_nt_chain(all + k0, dep2, nall - k0, reinterpret_cast<int*>(r.scratch + bb.flags), r.st));
+        break;
       }
+      int k1 = k0 + 1;
+      while (k1 < nall && layer_of[k1] == layer_of[k0]) ++k1;
+      GIB_TRY(gemm_nt_group(all + k0, k1 - k0, r.st));
+      k0 = k1;
     }
   }
   // ---- (C) input gradient of the first layer (may chain through a shared buffer via aux: keep the members in order)
