@@ -186,7 +186,7 @@ int gemm_nt(const GemmNT& p, cudaStream_t st) {
   }
   // narrow outputs over a long reduction (the APD heads: 1024 x 500 -> 39 / 3 / 1): a handful of tensor-core tiles
   // beat the SIMT kernel's few blocks walking all of K (measured 51 us -> see profiles/r02_launch_table_c2.txt)
-  if (g_use_tc && use_tc3() && p.N < 48 && p.K >= 128 && p.M >= 256 && tc3_eligible(p))
+  if (g_use_tc && use_tc3() && !(g_tc_debug & 4) && p.N < 48 && p.K >= 128 && p.M >= 256 && tc3_eligible(p))
     return gemm_nt_tc3_group(&p, 1, st);
   return gemm_nt_simt(p, st);
 }

@@ -188,13 +188,21 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
   hi = to_tf32(x);
   lo = to_tf32(x - __uint_as_float(hi));
 }
-// truncation split for the activation operand: hi = the top 19 bits (what the tensor core reads anyway), lo = x - hi
-// (exact in fp32; the tensor core reads its top 19 bits): 2 ALU ops per element.  The splitter warps sit on the
-// critical path of every k-block and share their issue slots with two epilogue warps each -- with the 7-op split
-// they fell behind the MMAs whenever the epilogue was busy (profiles/r02_tc3_probe.md).  Error of the pair:
-// <= 2^-21 |x| instead of 2^-22 |x|, far below the tensor core's truncating accumulation.
+// truncation split, used for the weight-gradient mode's X tile (the B operand, which stays in shared memory): hi = the
+// top 19 bits -- the raw tile already IS the hi operand, only lo is written -- lo = x - hi (exact in fp32; the tensor
+// core reads its top 19 bits): 2 ALU ops per element.  Error of the pair <= 2^-21 |x|, one-sided.
 __device__ __forceinline__ void split_tf32_fast(float x, uint32_t& hi, uint32_t& lo) {
   hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+// Split for the operand that travels through registers into tensor memory: hi rounded to NEAREST (ties away, what
+// cvt.rna does, as integer arithmetic: + half an ulp of the 10-bit mantissa, clear 13 bits; inf stays inf), lo = x - hi
+// exact.  With hi = trunc(x), lo always carries the sign of x and the tensor core's truncation of lo is a systematic
+// bias towards zero that adds up linearly over K (measured on the shipped checkpoint: logit error 7e-5 -> 1.1e-4 once
+// the 500-term output layers ran here); with hi rounded to nearest the sign of lo is random and the truncation of lo
+// is unbiased.  3 ALU ops per element instead of 2, no conversion-unit instruction.
+__device__ __forceinline__ void split_tf32_rn(float x, uint32_t& hi, uint32_t& lo) {
+  hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
   lo = __float_as_uint(x - __uint_as_float(hi));
 }
 template <bool RNA> __device__ __forceinline__ void split_act(float x, uint32_t& hi, uint32_t& lo) {
@@ -487,7 +495,7 @@ tc3_gemm_kernel(const __grid_constant__ Maps maps, const Params P) {
           for (int m = 0; m < 32; ++m) split_act<true>(v[m], hi[m], lo[m]);
         } else {
 #pragma unroll
-          for (int m = 0; m < 32; ++m) split_act<false>(v[m], hi[m], lo[m]);
+          for (int m = 0; m < 32; ++m) split_tf32_rn(v[m], hi[m], lo[m]);
         }
         tmem_st32(trow + stage * A_STAGE_COLS, hi);
         tmem_st32(trow + stage * A_STAGE_COLS + 32, lo);

@@ -84,7 +84,8 @@ int gib_version(void);
 /* tcgen05 3xTF32 GEMM path on (default) / off (fp32 SIMT GEMMs only); process-wide switch */
 void gib_set_tensor_cores(int on);
 int gib_get_tensor_cores(void);
-/* bit 1: no dependent-chain launches (every MLP layer its own launch).
+/* bit 2: narrow outputs (N < 48) stay on the fp32 SIMT kernel.
+ * bit 1: no dependent-chain launches (every MLP layer its own launch).
  * bit 0: route the dense GEMMs to the first-generation tcgen05 kernel (operand split through shared memory,
  * gemm_tc.cu) instead of the default second-generation one (activation operand through tensor memory, gemm_tc3.cu);
  * process-wide, A/B measurements only.  Capacity mode needs the default. */
