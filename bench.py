@@ -311,8 +311,8 @@ def scatter_roofline(pk):
     ms_grouped = _time_scatter(S, E, ld, ent_grouped)
     gbs = nbytes / ms_grouped / 1e6
     return {"kernel": "scatter_sum_kernel (K2)", "bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s",
-            "frac": gbs / pk["hbm"], "traffic": 208559360,
-            "traffic_source": "profiles/r01_ncu_full_summary.md (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum, one launch)",
+            "frac": gbs / pk["hbm"], "traffic": 194499328,
+            "traffic_source": "profiles/r02_ncu_tc3_stage5.md, r2k_scatter (ncu --set full: dram__bytes_read.sum 159.86 MB + dram__bytes_write.sum 34.64 MB, one launch of the streaming-hint variant; round 1, default caching: 208.56 MB)",
             "peak_source": pk["source"] + " (copy, burst)",
             "shape": {"slots": S, "entries": E, "width": width, "ld": ld},
             "layout": "bond-type-grouped message rows (the model's layout: entry index is an indirection)",
@@ -397,6 +397,14 @@ def run_b200_arm(args):
     torch.manual_seed(0)                      # identical random-init replicas on every rank
     net = mpnn.create(C).to(dev)
     dp_err = dp_gradient_check(net, cfg, world, rank, dev) if world > 1 else None
+    dp_err_fp32 = None
+    if world > 1:
+        # the same check with the fp32 SIMT GEMMs: isolates the data-parallel plumbing (sharding, loss scaling,
+        # all-reduce) from the tensor cores' 3xTF32 rounding, which differs between a shard and the whole batch
+        from graphinvent_b200._lib import lib as _l
+        _l.gib_set_tensor_cores(0)
+        dp_err_fp32 = dp_gradient_check(net, cfg, world, rank, dev)
+        _l.gib_set_tensor_cores(1)
     opt = FlatAdam(net.parameters(), lr=1e-4)
     entries = int((edges_h != 0).sum())
     cap = int(entries * 1.05) + 256           # static bond-entry capacity of the captured step
@@ -618,6 +626,7 @@ def run_b200_arm(args):
             "clocks": clocks, "roofline": roofline, "final_loss": final_loss}
     if dp_err is not None:
         line["dp_grad_rel_err"] = dp_err
+        line["dp_grad_rel_err_fp32_gemms"] = dp_err_fp32
         line["dp_grad_check"] = ("||allreduce_r(grad of shard r of a fixed 256-molecule batch) - grad of the whole batch on "
                                  "rank 0||_2 / ||.||_2, module API, before the timed regions")
     if single is not None:

@@ -84,7 +84,7 @@ int gib_version(void);
 /* tcgen05 3xTF32 GEMM path on (default) / off (fp32 SIMT GEMMs only); process-wide switch */
 void gib_set_tensor_cores(int on);
 int gib_get_tensor_cores(void);
-/* bit 2: narrow outputs (N < 48) stay on the fp32 SIMT kernel.
+/* bit 2: narrow outputs (N < 48, the APD heads) on the tensor-core kernel too (default: fp32 SIMT, see gemm_simt.cu).
  * bit 1: no dependent-chain launches (every MLP layer its own launch).
  * bit 0: route the dense GEMMs to the first-generation tcgen05 kernel (operand split through shared memory,
  * gemm_tc.cu) instead of the default second-generation one (activation operand through tensor memory, gemm_tc3.cu);
