@@ -61,6 +61,22 @@ class GraphGenerator:
         self._counters = z(2, dt=torch.int32)
         self._scratch = torch.empty(lib.gib_generation_scratch_bytes(B), dtype=torch.uint8, device=dev)
 
+    def _model_inputs(self, model):
+        """(nodes, edges) to evaluate `model` on.  The dummy graph in slot 0 is never reset (GraphGenerator.py:461-465
+        re-arms nodes / n_nodes only) and accumulates every action it samples: two "add" actions with different bond
+        types leave a bond with two non-zero types there.  The reference's AggregationMPNN / EMN prologues then fail
+        with a shape mismatch (aggregation_mpnn.py:115-141, edge_mpnn.py:123-156) and the whole generation run dies;
+        AttentionGGNN here rejects such input too.  Nothing ever reads the dummy slot's output, so for that model the
+        dummy graph is evaluated with the first non-zero type of each bond only (a copy: the state machine keeps the
+        reference's state of slot 0 bit for bit)."""
+        if getattr(model, "MODEL", None) != "AttGGNN":
+            return self.nodes, self.edges
+        e0 = self.edges[0]
+        nz = e0 != 0
+        edges = self.edges.clone()
+        edges[0] = e0 * (nz & (nz.to(torch.int32).cumsum(-1) == 1)).to(e0.dtype)
+        return self.nodes, edges
+
     @torch.no_grad()
     def build_graphs(self, replay=None, generator=None):
         """replay: optional iterable of (action int32 [B], likelihood float32 [B]) per round (the model is then not
@@ -83,7 +99,7 @@ class GraphGenerator:
                 action = action.to(self.device, torch.int32).contiguous()
                 lik = lik.to(self.device, torch.float32).contiguous()
             else:
-                out = self.model(self.nodes, self.edges)          # GraphGenerator.py:121
+                out = self.model(*self._model_inputs(self.model))    # GraphGenerator.py:121
                 action, lik = Fn.sample_actions(out, generator=generator)
             check(lib.gib_generation_round(B, self.N, self.F, self.Ef, self.A, self.CH, rnd, _ptr(action), _ptr(lik),
                                            _ptr(self.nodes), _ptr(self.edges), _ptr(self.n_nodes),
@@ -148,7 +164,9 @@ class GraphGeneratorRL(GraphGenerator):
                 raise RuntimeError("generation needs more than 2*max_n_nodes rounds: the per-slot likelihood buffer "
                                    "(GraphGeneratorRL.py:175, 'the 2 is arbitrary') would overflow, as in the reference")
             # the round kernel edits the batch in place while autograd keeps the inputs of every round: snapshot them
-            nodes_in, edges_in = self.nodes.clone(), self.edges.clone()
+            nodes_in, edges_in = self.nodes.clone(), self._model_inputs(agent)[1].clone()
+            if getattr(prior, "MODEL", None) == "AttGGNN" and getattr(agent, "MODEL", None) != "AttGGNN":
+                edges_in = self._model_inputs(prior)[1].clone()
             graph = Fn.build_graph(agent, edges_in) if share else None
             out_a = agent(nodes_in, edges_in, graph=graph) if share else agent(nodes_in, edges_in)   # GraphGeneratorRL.py:131-132
             out_p = prior(nodes_in, edges_in, graph=graph) if share else prior(nodes_in, edges_in)

@@ -157,3 +157,28 @@ def test_sampling_with_the_pretrained_checkpoint_builds_molecules():
     atoms = (nodes.sum(-1) > 0).sum(-1)
     assert torch.equal(atoms.to(torch.int8), n_nodes)
     assert torch.equal(edges, edges.transpose(1, 2))
+
+
+@pytest.mark.gpu
+def test_attention_ggnn_generation_survives_a_multi_type_bond_in_the_dummy_slot():
+    """Slot 0 (the dummy graph) is never reset and accumulates every action it samples: two "add" actions with
+    different bond types leave a bond with two non-zero types, on which the reference's AggregationMPNN prologue (and
+    this package's AttentionGGNN) raise.  The generator evaluates the dummy graph on a sanitised copy instead of dying
+    and keeps the reference's state of slot 0."""
+    from graphinvent_b200.config import make_constants
+    from graphinvent_b200.generation import GraphGenerator
+    from graphinvent_b200.gnn import mpnn
+    C = make_constants("AttGGNN")
+    torch.manual_seed(3)
+    net = mpnn.create(C).cuda().eval()
+    gen = GraphGenerator(net, batch_size=64, n_atom_types=5, n_formal_charge=3)
+    # the state after the dummy graph sampled add(bond_to=0, single) and add(bond_to=0, double) in two rounds
+    gen.nodes[0, 1, 0] = 1.0; gen.nodes[0, 1, 6] = 1.0
+    for t in (0, 1):
+        gen.edges[0, 0, 1, t] = 1.0; gen.edges[0, 1, 0, t] = 1.0
+    with pytest.raises(RuntimeError):               # the raw state is what the module itself rejects
+        net(gen.nodes, gen.edges)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    (nodes, edges, n_nodes), flat, final, proper = gen.sample(generator=g)
+    assert nodes.shape[0] == 64 and torch.isfinite(final).all()
+    assert ((gen.edges[0] != 0).sum(-1) > 1).any().item()          # slot 0 keeps its (reference) state
