@@ -507,14 +507,15 @@ def run_b200_arm(args):
         per = nrec // prof_steps if nrec > 0 and nrec % prof_steps == 0 and nrec <= cap_ else 0
         with open(args.launch_table, "w") as fh:
             fh.write(f"# {cfg}: timed launches of one eager forward + loss + backward (mean of {prof_steps} steps), "
-                     "launch order; class 0 = forward/dX GEMM launch (a chain = several layers), 1 = dW partials, 2 = K2\n")
+                     "launch order; class 0 = tcgen05 forward/dX GEMM launch (a chain = several layers), 1 = tcgen05 dW "
+                     "partials, 2 = K2, 3 / 4 = forward/dX and dW GEMMs on the fp32 SIMT kernels\n")
             fh.write("idx class  GFLOP_or_MB      us     TFLOP/s_or_GB/s\n")
             for i in range(per):
                 t = sum(rms[i + k * per] for k in range(prof_steps)) / prof_steps
                 wk = rwork[i]
-                rate = wk / (t * 1e-3) / (1e12 if rcls[i] < 2 else 1e9) if t > 0 else 0.0
-                fh.write(f"{i:3d} {rcls[i]:5d} {wk / (1e9 if rcls[i] < 2 else 1e6):12.3f} {t * 1e3:8.1f} {rate:10.1f}\n")
-    pms = (ctypes.c_double * 3)(); pwork = (ctypes.c_double * 3)(); pcnt = (ctypes.c_longlong * 3)()
+                rate = wk / (t * 1e-3) / (1e12 if rcls[i] != 2 else 1e9) if t > 0 else 0.0
+                fh.write(f"{i:3d} {rcls[i]:5d} {wk / (1e9 if rcls[i] != 2 else 1e6):12.3f} {t * 1e3:8.1f} {rate:10.1f}\n")
+    pms = (ctypes.c_double * 5)(); pwork = (ctypes.c_double * 5)(); pcnt = (ctypes.c_longlong * 5)()
     check(lib.gib_profile_collect(pms, pwork, pcnt), "profile_collect")
     lib.gib_profile_enable(0)
     for p_, v_ in zip(step.params, step.views):          # the eager passes replaced .grad: hand the bucket views back
@@ -595,7 +596,9 @@ def run_b200_arm(args):
                 "frac": gemm_tflops / tensor_peak, "traffic": None,
                 "peak_source": pk["source"] + " bf16 sustained / 2 (TF32 rate) / 3 (fp32-accurate 3xTF32 issue)",
                 "launches_timed": int(pcnt[cls]), "ms_in_class": pms[cls], "steps_timed": prof_steps,
-                "how": "eager exact-size pass (module API forward + loss + backward) over the same kernels, CUDA-event pair per launch",
+                "how": "eager exact-size pass (module API forward + loss + backward) over the same kernels, CUDA-event pair per "
+                       "launch; `achieved` = algorithmic FLOPs of the launches of THIS kernel / their summed durations "
+                       "(the fp32 SIMT GEMM launches are listed separately under `classes`)",
                 "share_of_step": pms[cls] / ms_instr, "ms_per_step_instrumented": ms_instr / prof_steps,
                 "classes": {"gemm_nt": {"ms_per_step": pms[0] / prof_steps, "tflops": tf(0), "frac": tf(0) / tensor_peak,
                                         "launches_per_step": pcnt[0] / prof_steps},
@@ -603,7 +606,19 @@ def run_b200_arm(args):
                                         "launches_per_step": pcnt[1] / prof_steps,
                                         "note": "main-stream part (partials); the reductions overlap on the side stream"},
                             "scatter": {"ms_per_step": pms[2] / prof_steps, "launches_per_step": pcnt[2] / prof_steps,
-                                        "gbs_8d_bytes": (pwork[2] / pms[2] / 1e6) if pms[2] else None}}}
+                                        "gbs_8d_bytes": (pwork[2] / pms[2] / 1e6) if pms[2] else None},
+                            "gemm_nt_fp32_simt": {"ms_per_step": pms[3] / prof_steps, "tflops": tf(3),
+                                                  "launches_per_step": pcnt[3] / prof_steps,
+                                                  "note": "narrow / tiny forward + dX problems on sgemm_nt_kernel (APD "
+                                                          "output layers, K < 32): a different kernel, not in `achieved`"},
+                            "gemm_dw_fp32_simt": {"ms_per_step": pms[4] / prof_steps, "tflops": tf(4),
+                                                  "launches_per_step": pcnt[4] / prof_steps},
+                            "all_forward_dx_gemm_launches": {
+                                "ms_per_step": (pms[0] + pms[3]) / prof_steps,
+                                "tflops": ((pwork[0] + pwork[3]) / (pms[0] + pms[3]) / 1e9) if pms[0] + pms[3] else 0.0,
+                                "frac": ((pwork[0] + pwork[3]) / (pms[0] + pms[3]) / 1e9 / tensor_peak) if pms[0] + pms[3] else 0.0,
+                                "note": "tcgen05 and fp32 SIMT launches together (the round-1 / earlier round-2 definition "
+                                        "of the class)"}}}
     line = {"metric": metric_name(cfg), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": W, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -676,7 +691,7 @@ def k2_in_model(pk, dev):
     for _ in range(2):
         one()
     torch.cuda.synchronize()
-    pms = (ctypes.c_double * 3)(); pwork = (ctypes.c_double * 3)(); pcnt = (ctypes.c_longlong * 3)()
+    pms = (ctypes.c_double * 5)(); pwork = (ctypes.c_double * 5)(); pcnt = (ctypes.c_longlong * 5)()
     check(lib.gib_profile_collect(pms, pwork, pcnt), "profile_collect")
     lib.gib_profile_enable(0)
     gbs = pwork[2] / pms[2] / 1e6 if pms[2] else 0.0

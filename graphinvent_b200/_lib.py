@@ -29,7 +29,7 @@ MODEL_ID = {"GGNN": 0, "MNN": 1, "AttGGNN": 2, "EMN": 3}
 HDR_INTS = 16
 HDR_E, HDR_P, HDR_TYPE_COUNT, HDR_TYPE_BASE, HDR_FLAGS, HDR_CAPACITY = 0, 1, 2, 6, 11, 12
 FLAG_MULTITYPE, FLAG_NONBINARY, FLAG_OVERFLOW = 1, 2, 4
-ABI_VERSION = 200      # must equal gib_version() of the loaded library (include/gib200.h)
+ABI_VERSION = 201      # must equal gib_version() of the loaded library (include/gib200.h)
 
 _PROTOS = {
     "gib_last_error": (ctypes.c_char_p, []),

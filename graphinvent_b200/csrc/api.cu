@@ -141,7 +141,7 @@ using namespace gib;
 extern "C" {
 
 const char* gib_last_error(void) { return g_err; }
-int gib_version(void) { return 200; }   // 200: capacity mode, int8 inputs, second-generation tcgen05 GEMM, grouped dW
+int gib_version(void) { return 201; }   // 200: capacity mode, int8 inputs, second-generation tcgen05 GEMM, grouped dW; 201: 5 profile classes
 void gib_set_tensor_cores(int on) { g_use_tc = on != 0; }
 int gib_get_tensor_cores(void) { return g_use_tc ? 1 : 0; }
 void gib_tc_debug(int mode) { g_tc_debug = mode; }

@@ -237,7 +237,7 @@ int gemm_nt_simt(const GemmNT& p, cudaStream_t st) {
     set_error("gemm_nt: K=%d lda=%d ldb=%d violate the padded-layout contract", p.K, p.lda, p.ldb);
     return -2;
   }
-  ProfScope prof(PROF_GEMM_NT, p.work > 0 ? p.work : 2.0 * p.M * (double)p.N * p.K, st);
+  ProfScope prof(PROF_GEMM_NT_SIMT, p.work > 0 ? p.work : 2.0 * p.M * (double)p.N * p.K, st);
   const long long ctas_big = (long long)ceil_div(p.M, 128) * ceil_div(p.N, 128);
   const int num_sms = device_sm_count();
   if (ctas_big >= num_sms && p.N > 64) {
@@ -643,7 +643,7 @@ int gemm_dw(const GemmDW& q, cudaStream_t st) {
   if (q.m_dev || (g_use_tc && use_tc3() && q.dW && q.M >= 2048 && q.Nn >= 32 && q.Kk >= 32 && tc3_dw_eligible(q) &&
                   q.half_floats > 0))
     return gemm_dw_group(&q, 1, 0, st);
-  ProfScope prof(PROF_GEMM_DW, q.work > 0 ? q.work : 2.0 * q.M * (double)q.R * q.C, st);
+  ProfScope prof(g_use_tc && !use_tc3() ? PROF_GEMM_DW : PROF_GEMM_DW_SIMT, q.work > 0 ? q.work : 2.0 * q.M * (double)q.R * q.C, st);
   DwSide* d;
   GIB_TRY(dw_side(&d));
   const int half = (int)(d->calls++ & 1);

@@ -6,7 +6,10 @@
 
 namespace gib {
 
-enum ProfClass : int { PROF_GEMM_NT = 0, PROF_GEMM_DW = 1, PROF_SCATTER = 2, PROF_NCLASS = 3 };
+// 0 / 1: launches of the tcgen05 kernels (forward + dX, weight gradients); 3 / 4: the same contracts on the fp32 SIMT
+// kernels (narrow / tiny problems, and everything when tensor cores are off)
+enum ProfClass : int { PROF_GEMM_NT = 0, PROF_GEMM_DW = 1, PROF_SCATTER = 2, PROF_GEMM_NT_SIMT = 3, PROF_GEMM_DW_SIMT = 4,
+                       PROF_NCLASS = 5 };
 
 extern bool g_prof_on;
 void prof_begin(int cls, double work, cudaStream_t st);

@@ -222,8 +222,10 @@ int gib_generation_round(int B, int N, int F, int Ef, int n_atom_types, int n_ch
                          void* scratch, gib_stream stream);
 
 /* ---- measurement hooks: CUDA-event timing per kernel class on the launching stream.
- *      class 0 = forward/dX GEMMs, 1 = dW GEMMs (+ split-K reduce), 2 = scatter-aggregate (K2).
- *      work = algorithmic FLOPs (classes 0,1) or bytes (class 2).  Collect after a stream sync. -- */
+ *      class 0 = forward/dX launches of the tcgen05 kernel, 1 = its weight-gradient launches, 2 = scatter-aggregate (K2),
+ *      3 / 4 = forward/dX and weight-gradient GEMMs on the fp32 SIMT kernels.  GIB_PROFILE_CLASSES entries per array.
+ *      work = algorithmic FLOPs (GEMM classes) or bytes (class 2).  Collect after a stream sync. -- */
+#define GIB_PROFILE_CLASSES 5
 void gib_profile_enable(int on);
 long long gib_launch_count(void); /* kernels launched by this library since load */
 int gib_profile_collect(double* ms, double* work, long long* count);
