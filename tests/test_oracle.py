@@ -128,3 +128,18 @@ def test_reference_aggregation_mpnn_rejects_multi_type_bonds():
         net(nodes, edges)
     ggnn = refimpl.build(O.make_constants("GGNN"))          # the summation family handles it (sum over the types)
     assert torch.isfinite(ggnn(nodes, edges)).all()
+
+
+def test_reference_edge_mpnn_rejects_multi_type_bonds():
+    """the reference's EMN fails on such a bond too: `edge_degrees` sums the bond VALUES (edge_mpnn.py:123) while the
+    incoming-edge lists come from `nonzero()` (:118-121), so the comparison at :156 raises a shape mismatch.  In the
+    reference generator this state is reachable only in the never-reset dummy graph of slot 0 -- the
+    reason `tools/bench_generation.py` retries seeds for its CPU leg."""
+    from tests import refimpl
+    if not refimpl.available():
+        pytest.skip("/root/reference not mounted")
+    C = O.make_constants("EMN")
+    net = refimpl.build(C)
+    nodes, edges = _multitype_batch(C)
+    with pytest.raises(RuntimeError):
+        net(nodes, edges)
