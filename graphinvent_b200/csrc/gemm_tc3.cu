@@ -11,20 +11,22 @@
 // 128 B/clk -- and the first-generation kernel (gemm_tc.cu) added the TMA writes and an in-place hi/lo split on top:
 // 192-224 KB of shared-memory traffic per 32-float k-block against 768 MMA cycles (measured: tensor pipe 25 % busy,
 // profiles/r01_ncu_full_summary.md).  Here a k-block costs: TMA writes 48 KB (raw A tile, W hi, W lo), one 16 KB read
-// by the splitter warps, and 12 x 4 KB of W reads by the MMAs = 112 KB = 896 cycles against the same 768.
+// by the splitter warps, and 48 KB of W reads by the MMAs = 112 KB = 896 cycles against the same 768.
 //
 // Roles (448 threads, one persistent CTA per SM, 4-stage ring; smem 3 x 16 KB per stage):
 //   warp 0      TMA producer   raw A tile [128 x 32 fp32, 128B swizzle] + W_hi / W_lo tiles (TN: G and X tiles)
-//   warps 2-5   splitters      thread = tile row: 8 x LDS.128 (swizzle decoded -> conflict free), hi = rna_tf32(x),
-//                              lo = rna_tf32(x - hi), two tcgen05.st.32x32b.x32 into the stage's 64 TMEM columns.
+//   warps 2-5   splitters      thread = tile row: 8 x LDS.128 (swizzle decoded -> conflict free), hi = x rounded to
+//                              nearest at 10 mantissa bits (integer add + mask), lo = x - hi (exact), two
+//                              tcgen05.st.32x32b.x32 into the stage's 64 TMEM columns.
 //                              TN: thread = column n of G (register transpose for free), masks rows beyond the valid
-//                              count, accumulates the bias column sum, and splits the X tile in place (MN-major B)
-//   warp 1      MMA issuer     per k-block 12 x tcgen05.mma.kind::tf32 with A in TMEM: hi*hi into the main
-//                              accumulator, lo*hi + hi*lo into a second one (their roundings stay away from the large
-//                              sum; summed in fp32 in the epilogue)
+//                              count, accumulates the bias column sum; the X tile (MN-major B) is split in place by
+//                              the epilogue warps, which idle during a work item's k-loop
+//   warp 1      MMA issuer     per k-block 8 x tcgen05.mma.kind::tf32 with A in TMEM: a_hi * [W_hi | W_lo] as ONE N = 256
+//                              instruction (hi*hi into the main accumulator, hi*lo into the second one) + a_lo * W_hi;
+//                              the cross terms' roundings stay away from the large sum (summed in fp32 in the epilogue)
 //   warps 6-13  epilogue       drain both accumulators into registers (then the MMA warp may start the next tile),
 //                              XOR-swizzled per-warp smem transpose (conflict free, explicit LDS/STS), bias / SELU /
-//                              dSELU / residual in the coalesced domain, 128-bit global stores
+//                              dSELU / residual in the coalesced domain (branch-free), 128-bit global stores of full lines
 // TMEM (512 columns): [0,128) main accumulator, [128,256) cross-term accumulator, [256,512) 4 x (A_hi 32 | A_lo 32).
 //
 // Dynamic row counts: a problem may name device ints (m_dev, base_dev) -- the bond-type group sizes written by K0 --
